@@ -1,0 +1,381 @@
+"""CPU oracle for the deepards cnn_linear hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``deepards_b200/`` may import this
+module; it is used by ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` as the checker and
+as the timed CPU baseline -- never as the product path.
+
+What it is: a functional, fp32, torch-CPU restatement of the reference's module
+graph for this path.  The reference has no arithmetic of its own -- every
+operation is a ``torch.nn`` library call -- so the
+restatement is "the same library calls in the same order on an explicit
+``state_dict``", written without any ``nn.Module`` so that nothing of the
+reference's class structure is needed at run time (``/root/reference`` does not
+exist on the GPU box).
+
+Pinned against: the reference's own modules imported from ``/root/reference``
+(``oracle/make_golden.py`` generates ``tests/golden/*.npz`` from them; the CPU
+test-suite checks this oracle against those files).  The reference's test-suite
+holds no golden vector for this path, so these generated
+vectors are the pin.
+
+Reference call sites restated here
+  * ResNet stem / stages / pooling ........ deepards/models/resnet.py:141-163
+  * BasicBlock ............................ deepards/models/resnet.py:24-40
+  * downsample (conv1x1 stride s + BN) .... deepards/models/resnet.py:125-131
+  * DenseNet features / head pooling ...... deepards/models/densenet.py:117-150, 179-193
+  * _DenseLayer ........................... deepards/models/densenet.py:18-43
+  * _Transition ........................... deepards/models/densenet.py:68-80
+  * CNNLinearNetwork.forward .............. deepards/models/torch_cnn_linear_network.py:104-113
+  * CNNSingleBreathLinearNetwork.forward .. deepards/models/torch_cnn_linear_network.py:57-67
+  * BCEWithLogits loss .................... deepards/train_ards_detector.py:530, 929-930
+  * gradient clamp hook ................... deepards/train_ards_detector.py:474-476
+  * GradCAM forward/backward .............. deepards/gradcam.py:40-65, 83-107
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+SEQ_LEN = 224
+
+
+# --------------------------------------------------------------------------
+# parameter construction (names are the reference's state_dict keys)
+# --------------------------------------------------------------------------
+def _conv_w(gen, cout, cin, k):
+    # He-normal with fan = k * cout (resnet.py:115-118, densenet.py:156-159)
+    std = math.sqrt(2.0 / (k * cout))
+    return torch.randn(cout, cin, k, generator=gen, dtype=torch.float32) * std
+
+
+def _bn(sd, name, c, running, gen=None, perturb=0.0):
+    w = torch.ones(c)
+    b = torch.zeros(c)
+    if perturb and gen is not None:
+        # parity tests perturb gamma/beta so that a wrong affine is visible
+        w = w + perturb * torch.randn(c, generator=gen)
+        b = b + perturb * torch.randn(c, generator=gen)
+    sd[name + ".weight"] = w
+    sd[name + ".bias"] = b
+    if running:
+        sd[name + ".running_mean"] = torch.zeros(c)
+        sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+
+def _linear(sd, name, fin, fout, gen):
+    bound = 1.0 / math.sqrt(fin)
+    sd[name + ".weight"] = (torch.rand(fout, fin, generator=gen) * 2 - 1) * bound
+    sd[name + ".bias"] = (torch.rand(fout, generator=gen) * 2 - 1) * bound
+
+
+def resnet_state(seed: int = 0, layers: Sequence[int] = (2, 2, 2, 2), initial_planes: int = 64,
+                 bn_perturb: float = 0.0, prefix: str = "") -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of the reference's 1-D BasicBlock ResNet (resnet.py:83-139), incl.
+    the never-used conv1_alt/conv2/bn2 (resnet.py:90-96).  Deterministic in `seed`;
+    the values are this oracle's own draw with the reference's init distribution."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    p = initial_planes
+    sd["conv1.weight"] = _conv_w(gen, p, 1, 7)
+    sd["conv1_alt.weight"] = _conv_w(gen, p, 1, 3)
+    _bn(sd, "bn1", p, True, gen, bn_perturb)
+    sd["conv2.weight"] = _conv_w(gen, p, p, 7)
+    _bn(sd, "bn2", p, True, gen, bn_perturb)
+    inpl = p
+    for li, nb in enumerate(layers, 1):
+        planes = p * 2 ** (li - 1)
+        for bi in range(nb):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            pre = "layer%d.%d." % (li, bi)
+            sd[pre + "conv1.weight"] = _conv_w(gen, planes, inpl, 3)
+            _bn(sd, pre + "bn1", planes, True, gen, bn_perturb)
+            sd[pre + "conv2.weight"] = _conv_w(gen, planes, planes, 3)
+            _bn(sd, pre + "bn2", planes, True, gen, bn_perturb)
+            if stride != 1 or inpl != planes:
+                sd[pre + "downsample.0.weight"] = _conv_w(gen, planes, inpl, 1)
+                _bn(sd, pre + "downsample.1", planes, True, gen, bn_perturb)
+            inpl = planes
+    if prefix:
+        sd = OrderedDict((prefix + k, v) for k, v in sd.items())
+    return sd
+
+
+def densenet_state(seed: int = 0, block_config: Sequence[int] = (2, 2, 2, 2), growth_rate: int = 32,
+                   num_init_features: int = 64, bn_size: int = 4, in_chans: int = 1,
+                   bn_perturb: float = 0.0, prefix: str = "") -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of the reference's 1-D DenseNet (densenet.py:96-167): no BN buffers
+    (track_running_stats=False, densenet.py:107)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["features.conv0.weight"] = _conv_w(gen, num_init_features, in_chans, 7)
+    _bn(sd, "features.norm0", num_init_features, False, gen, bn_perturb)
+    nf = num_init_features
+    for i, nl in enumerate(block_config, 1):
+        for j in range(1, nl + 1):
+            pre = "features.denseblock%d.denselayer%d." % (i, j)
+            cin = nf + (j - 1) * growth_rate
+            _bn(sd, pre + "norm1", cin, False, gen, bn_perturb)
+            sd[pre + "conv1.weight"] = _conv_w(gen, bn_size * growth_rate, cin, 1)
+            _bn(sd, pre + "norm2", bn_size * growth_rate, False, gen, bn_perturb)
+            sd[pre + "conv2.weight"] = _conv_w(gen, growth_rate, bn_size * growth_rate, 3)
+        nf = nf + nl * growth_rate
+        if i != len(block_config):
+            pre = "features.transition%d." % i
+            _bn(sd, pre + "norm", nf, False, gen, bn_perturb)
+            sd[pre + "conv.weight"] = _conv_w(gen, nf // 2, nf, 1)
+            nf = nf // 2
+    _bn(sd, "features.norm5", nf, False, gen, bn_perturb)
+    if prefix:
+        sd = OrderedDict((prefix + k, v) for k, v in sd.items())
+    return sd
+
+
+def backbone_out_filters(sd: Dict[str, torch.Tensor], prefix: str = "breath_block.") -> int:
+    if prefix + "features.norm5.weight" in sd:
+        return sd[prefix + "features.norm5.weight"].numel()
+    last = [k for k in sd if k.startswith(prefix + "layer4.") and k.endswith("bn2.weight")]
+    return sd[sorted(last)[-1]].numel()
+
+
+def cnn_linear_state(backbone: str = "resnet18", seed: int = 0, sub_batch: int = 20, per_breath: bool = False,
+                     bn_perturb: float = 0.0, **kw) -> "OrderedDict[str, torch.Tensor]":
+    """state_dict of CNNLinearNetwork(backbone(), sub_batch, 0) (torch_cnn_linear_network.py:97-102)
+    or, with per_breath, CNNSingleBreathLinearNetwork (torch_cnn_linear_network.py:50-55)."""
+    if backbone.startswith("resnet"):
+        sd = resnet_state(seed, bn_perturb=bn_perturb, prefix="breath_block.", **kw)
+    elif backbone.startswith("densenet"):
+        sd = densenet_state(seed, bn_perturb=bn_perturb, prefix="breath_block.", **kw)
+    else:
+        raise ValueError(backbone)
+    f = backbone_out_filters(sd)
+    gen = torch.Generator().manual_seed(seed + 7919)
+    _linear(sd, "linear_final", f if per_breath else f * sub_batch, 2, gen)
+    return sd
+
+
+# --------------------------------------------------------------------------
+# forward graphs
+# --------------------------------------------------------------------------
+def _batchnorm(x, sd, name, running_update: bool):
+    """nn.BatchNorm1d in training mode on ONE sub-batch: biased batch variance for the
+    normalisation, eps 1e-5; running buffers (if the layer has them and running_update
+    is set) get momentum 0.1 with the unbiased variance -- exactly F.batch_norm."""
+    rm = sd.get(name + ".running_mean") if running_update else None
+    rv = sd.get(name + ".running_var") if running_update else None
+    y = F.batch_norm(x, rm, rv, sd[name + ".weight"], sd[name + ".bias"], True, BN_MOMENTUM, BN_EPS)
+    if rm is not None and (name + ".num_batches_tracked") in sd:
+        sd[name + ".num_batches_tracked"].add_(1)
+    return y
+
+
+def resnet_forward(sd, x, prefix: str = "", first_pool_type: str = "max", double_conv_first: bool = False,
+                   running_update: bool = False):
+    """(N, 1, 224) -> (N, 8*initial_planes); BN statistics over the whole N (resnet.py:141-163)."""
+    g = lambda k: sd[prefix + k]
+    bn = lambda t, name: _batchnorm(t, _Prefixed(sd, prefix), name, running_update)
+    if not double_conv_first:
+        y = F.conv1d(x, g("conv1.weight"), stride=2, padding=3)
+        y = bn(y, "bn1")
+    else:
+        y = F.conv1d(x, g("conv1_alt.weight"), stride=1, padding=1)
+        y = bn(y, "bn1")
+        y = F.conv1d(y, g("conv2.weight"), stride=2, padding=3)
+        y = bn(y, "bn2")
+    y = F.relu(y)
+    if first_pool_type == "max":
+        y = F.max_pool1d(y, 3, 2, 1)
+    else:
+        y = F.avg_pool1d(y, 3, 2, 1)
+    li = 1
+    while (prefix + "layer%d.0.conv1.weight" % li) in sd:
+        bi = 0
+        while (prefix + "layer%d.%d.conv1.weight" % (li, bi)) in sd:
+            pre = "layer%d.%d." % (li, bi)
+            stride = 2 if (li > 1 and bi == 0) else 1
+            out = F.conv1d(y, g(pre + "conv1.weight"), stride=stride, padding=1)
+            out = F.relu(bn(out, pre + "bn1"))
+            out = F.conv1d(out, g(pre + "conv2.weight"), stride=1, padding=1)
+            out = bn(out, pre + "bn2")
+            if (prefix + pre + "downsample.0.weight") in sd:
+                res = F.conv1d(y, g(pre + "downsample.0.weight"), stride=stride)
+                res = bn(res, pre + "downsample.1")
+            else:
+                res = y
+            y = F.relu(out + res)
+            bi += 1
+        li += 1
+    y = F.avg_pool1d(y, 7, 1)
+    return y.reshape(y.shape[0], -1)
+
+
+class _Prefixed(dict):
+    """dict view that prepends a prefix on lookup (writes go through to the base tensors)."""
+
+    def __init__(self, base, prefix):
+        super().__init__()
+        self._b, self._p = base, prefix
+
+    def __getitem__(self, k):
+        return self._b[self._p + k]
+
+    def __contains__(self, k):
+        return (self._p + k) in self._b
+
+    def get(self, k, default=None):
+        return self._b.get(self._p + k, default)
+
+
+def densenet_features(sd, x, prefix: str = "", drop_rate: float = 0.0, training: bool = False):
+    """(N, C0, 224) -> (N, 128, 7): `DenseNet.features` (densenet.py:117-150).  BN always uses
+    batch statistics (track_running_stats=False).  Dropout only if drop_rate>0 and training."""
+    g = lambda k: sd[prefix + k]
+    bn = lambda t, name: F.batch_norm(t, None, None, g(name + ".weight"), g(name + ".bias"), True, 0.0, BN_EPS)
+    y = F.conv1d(x, g("features.conv0.weight"), stride=2, padding=3)
+    y = F.relu(bn(y, "features.norm0"))
+    y = F.max_pool1d(y, 3, 2, 1)
+    i = 1
+    while (prefix + "features.denseblock%d.denselayer1.conv1.weight" % i) in sd:
+        j = 1
+        while (prefix + "features.denseblock%d.denselayer%d.conv1.weight" % (i, j)) in sd:
+            pre = "features.denseblock%d.denselayer%d." % (i, j)
+            t = F.relu(bn(y, pre + "norm1"))
+            t = F.conv1d(t, g(pre + "conv1.weight"))
+            t = F.relu(bn(t, pre + "norm2"))
+            t = F.conv1d(t, g(pre + "conv2.weight"), padding=1)
+            if drop_rate > 0:
+                t = F.dropout(t, p=drop_rate, training=training)
+            y = torch.cat([y, t], 1)
+            j += 1
+        pre = "features.transition%d." % i
+        if (prefix + pre + "conv.weight") in sd:
+            t = F.relu(bn(y, pre + "norm"))
+            t = F.conv1d(t, g(pre + "conv.weight"))
+            y = F.avg_pool1d(t, 2, 2)
+        i += 1
+    return bn(y, "features.norm5")
+
+
+def densenet_forward(sd, x, prefix: str = "", **kw):
+    """densenet.py:179-189: relu(features) -> AvgPool1d(7) -> flatten."""
+    f = densenet_features(sd, x, prefix, **kw)
+    y = F.avg_pool1d(F.relu(f), 7, 1)
+    return y.reshape(f.shape[0], -1)
+
+
+def backbone_forward(sd, x, prefix: str = "breath_block.", **kw):
+    if (prefix + "features.conv0.weight") in sd:
+        kw.pop("running_update", None)
+        return densenet_forward(sd, x, prefix, **kw)
+    return resnet_forward(sd, x, prefix, **kw)
+
+
+def cnn_linear_forward(sd, x, per_breath: bool = False, **kw):
+    """The reference's per-sequence loop (torch_cnn_linear_network.py:104-113): each
+    x[i] of shape (20, C, 224) is one BatchNorm sub-batch.  Returns (B, 2), or
+    (B, 20, 2) for the per-breath head (torch_cnn_linear_network.py:57-67)."""
+    if x.shape[-1] != SEQ_LEN:
+        raise Exception("input breaths must have sequence length of 224")
+    w, b = sd["linear_final.weight"], sd["linear_final.bias"]
+    rows = []
+    for i in range(x.shape[0]):
+        feat = backbone_forward(sd, x[i], **kw)
+        if per_breath:
+            rows.append(F.linear(feat, w, b).unsqueeze(0))
+        else:
+            rows.append(F.linear(feat.reshape(-1), w, b).unsqueeze(0))
+    return torch.cat(rows, 0)
+
+
+def bce_with_logits(outputs, target):
+    """torch.nn.BCEWithLogitsLoss() (mean over all B*2 elements), train_ards_detector.py:530."""
+    return F.binary_cross_entropy_with_logits(outputs, target)
+
+
+def forward_backward(sd, x, target, clip_val: Optional[float] = None, per_breath: bool = False, **kw):
+    """One training step's forward + backward (train_ards_detector.py:153, 162-163) on leaf copies
+    of the floating-point parameters.  Returns (logits, loss, {name: grad}).  Parameters that
+    take no part in the graph (conv1_alt, conv2, bn2) get no entry, like `.grad is None`."""
+    leaves = OrderedDict()
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            leaves[k] = v.detach().clone().requires_grad_(True)
+        else:
+            leaves[k] = v
+    out = cnn_linear_forward(leaves, x, per_breath=per_breath, **kw)
+    loss = bce_with_logits(out, target)
+    names = [k for k, v in leaves.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    gd = OrderedDict()
+    for k, gr in zip(names, grads):
+        if gr is None:
+            continue
+        if clip_val is not None:
+            gr = gr.clamp(-clip_val, clip_val)  # the register_hook clamp, train_ards_detector.py:474-476
+        gd[k] = gr
+    return out.detach(), loss.detach(), gd
+
+
+def gradcam_forward_backward(sd, x, target: Optional[int] = None):
+    """gradcam.py:40-65, 83-99 for ONE sequence x:(20, 1, 224): returns A=(20,128,7) features,
+    dA (gradient of the chosen logit wrt A) and the (1,2) model output.  DenseNet only."""
+    prefix = "breath_block."
+    a = densenet_features(sd, x, prefix).detach().requires_grad_(True)
+    # the reference differentiates through `features` as well (parameters require grad); dA does
+    # not depend on that part of the graph, so the oracle cuts it here.
+    y = F.avg_pool1d(F.relu(a), 7, 1).reshape(-1)
+    out = F.linear(y, sd["linear_final.weight"], sd["linear_final.bias"]).unsqueeze(0)
+    if target is None:
+        target = int(out.argmax())
+    (da,) = torch.autograd.grad(out[0, target], a)
+    return a.detach(), da, out.detach()
+
+
+# --------------------------------------------------------------------------
+# batched formulation (same numbers, one pass over all B*20 breaths) -- used by the
+# tests to show "grouped BN with group = 20" == the reference loop
+# --------------------------------------------------------------------------
+def grouped_batchnorm(x, weight, bias, group: int):
+    """BatchNorm over groups of `group` consecutive rows of x:(N, C, L)."""
+    n, c, l = x.shape
+    xg = x.reshape(n // group, group, c, l)
+    mean = xg.mean(dim=(1, 3), keepdim=True)
+    var = xg.var(dim=(1, 3), unbiased=False, keepdim=True)
+    y = (xg - mean) / torch.sqrt(var + BN_EPS)
+    y = y * weight.view(1, 1, c, 1) + bias.view(1, 1, c, 1)
+    return y.reshape(n, c, l)
+
+
+# --------------------------------------------------------------------------
+# synthetic inputs
+# --------------------------------------------------------------------------
+DATASET_MU = 2.056
+DATASET_STD = 28.08
+
+
+def synthetic_breaths(n_seq: int, seed: int = 1234, sub_batch: int = 20) -> torch.Tensor:
+    """(n_seq, sub_batch, 1, 224) fp32 ventilator-flow-like windows, z-scored with the
+    dataset constants stored in the reference's tests/test_dataset.pkl."""
+    gen = torch.Generator().manual_seed(seed)
+    n = n_seq * sub_batch
+    ni = torch.randint(40, 81, (n, 1), generator=gen).float()
+    peak = 30.0 + 40.0 * torch.rand(n, 1, generator=gen)
+    t = torch.arange(SEQ_LEN, dtype=torch.float32).view(1, -1)
+    insp = peak * torch.sin(math.pi * t / ni)
+    exp_ = -0.6 * peak * torch.exp(-(t - ni) / 25.0)
+    flow = torch.where(t < ni, insp, exp_) + 1.5 * torch.randn(n, SEQ_LEN, generator=gen)
+    flow = (flow - DATASET_MU) / DATASET_STD
+    return flow.view(n_seq, sub_batch, 1, SEQ_LEN).contiguous()
+
+
+def synthetic_targets(n_seq: int, seed: int = 1234) -> torch.Tensor:
+    gen = torch.Generator().manual_seed(seed + 1)
+    cls = (torch.rand(n_seq, generator=gen) < 0.5).long()
+    return F.one_hot(cls, 2).float()
