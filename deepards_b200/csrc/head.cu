@@ -1,0 +1,283 @@
+// Pooling, dropout and the linear classification head: small bandwidth-bound kernels.
+#include "common.cuh"
+
+namespace dards {
+
+// ---- AvgPool1d(2,2): (N,L,C) -> (N,L/2,C) --------------------------------------------------------------
+template <typename T>
+__global__ void avgpool2_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, long long rows_out, int l_out, int c4,
+                                    int in_stride, int out_stride) {
+  long long total = rows_out * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cq = (int)(i % c4);
+    long long r = i / c4;  // n*l_out + q
+    long long n = r / l_out;
+    int q = (int)(r % l_out);
+    const T* src = in + ((size_t)(n * 2 * l_out) + 2 * q) * in_stride + cq * 4;
+    float4 a = Elem<T>::ld4(src), b = Elem<T>::ld4(src + in_stride);
+    Elem<T>::st4(out + (size_t)r * out_stride + cq * 4,
+                 make_float4(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z), 0.5f * (a.w + b.w)));
+  }
+}
+
+template <typename T>
+__global__ void avgpool2_bwd_kernel(const T* __restrict__ dout, T* __restrict__ din, long long rows_out, int l_out,
+                                    int c4, int dout_stride, int din_stride) {
+  long long total = rows_out * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cq = (int)(i % c4);
+    long long r = i / c4;
+    long long n = r / l_out;
+    int q = (int)(r % l_out);
+    float4 d = Elem<T>::ld4(dout + (size_t)r * dout_stride + cq * 4);
+    d.x *= 0.5f; d.y *= 0.5f; d.z *= 0.5f; d.w *= 0.5f;
+    T* dst = din + ((size_t)(n * 2 * l_out) + 2 * q) * din_stride + cq * 4;
+    Elem<T>::st4(dst, d);
+    Elem<T>::st4(dst + din_stride, d);
+  }
+}
+
+// ---- AvgPool1d(L) + flatten: (N,L,C) -> feat (N,C) fp32 --------------------------------------------------
+template <typename T>
+__global__ void avgpool_full_fwd_kernel(const T* __restrict__ in, float* __restrict__ feat, long long n_breaths, int l,
+                                        int c4, int in_stride) {
+  long long total = n_breaths * c4;
+  const float inv = 1.f / (float)l;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cq = (int)(i % c4);
+    long long n = i / c4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < l; ++q) {
+      float4 v = Elem<T>::ld4(in + ((size_t)n * l + q) * in_stride + cq * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+    *reinterpret_cast<float4*>(feat + (size_t)n * c4 * 4 + cq * 4) = s;
+  }
+}
+
+template <typename T>
+__global__ void avgpool_full_bwd_kernel(const float* __restrict__ dfeat, T* __restrict__ din, long long n_breaths, int l,
+                                        int c4, int din_stride) {
+  long long total = n_breaths * l * c4;
+  const float inv = 1.f / (float)l;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int cq = (int)(i % c4);
+    long long r = i / c4;  // n*l + q
+    long long n = r / l;
+    float4 d = *reinterpret_cast<const float4*>(dfeat + (size_t)n * c4 * 4 + cq * 4);
+    d.x *= inv; d.y *= inv; d.z *= inv; d.w *= inv;
+    Elem<T>::st4(din + (size_t)r * din_stride + cq * 4, d);
+  }
+}
+
+// ---- dropout: keep-mask is a pure function of (seed, element index) ---------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+  // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+
+template <typename T>
+__global__ void dropout_kernel(T* __restrict__ x, long long n_rows, int c, int stride, float p, float scale,
+                               unsigned long long seed, const unsigned long long* __restrict__ seed_off) {
+  if (seed_off) seed += *seed_off * 0x9E3779B97F4A7C15ull;
+  long long total = n_rows * c;
+  const uint32_t thresh = (uint32_t)(p * 4294967296.0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / c;
+    int cc = (int)(i % c);
+    T* ptr = x + (size_t)r * stride + cc;
+    uint32_t rnd = mix32(seed ^ ((uint64_t)i * 0xD1342543DE82EF95ull));
+    float v = Elem<T>::ld(ptr);
+    Elem<T>::st(ptr, rnd < thresh ? 0.f : v * scale);
+  }
+}
+
+// ---- linear head ----------------------------------------------------------------------------------------
+// logits[r][j] = bias[j] + sum_k feat[r][k] w[j][k]; one CTA per row, n_out <= 8
+constexpr int LIN_THREADS = 256;
+constexpr int LIN_MAX_OUT = 8;
+
+__global__ void __launch_bounds__(LIN_THREADS) linear_fwd_kernel(const float* __restrict__ feat,
+                                                                  const float* __restrict__ w,
+                                                                  const float* __restrict__ bias,
+                                                                  float* __restrict__ logits, int k, int n_out) {
+  __shared__ float red[LIN_THREADS / 32][LIN_MAX_OUT];
+  const int r = blockIdx.x;
+  float acc[LIN_MAX_OUT];
+#pragma unroll
+  for (int j = 0; j < LIN_MAX_OUT; ++j) acc[j] = 0.f;
+  const float* f = feat + (size_t)r * k;
+  for (int i = threadIdx.x; i < k; i += LIN_THREADS) {
+    float v = f[i];
+#pragma unroll
+    for (int j = 0; j < LIN_MAX_OUT; ++j)
+      if (j < n_out) acc[j] = fmaf(v, w[(size_t)j * k + i], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < LIN_MAX_OUT; ++j) acc[j] = warp_sum(acc[j]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < LIN_MAX_OUT; ++j) red[warp][j] = acc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < n_out) {
+    float s = bias[threadIdx.x];
+    for (int wv = 0; wv < LIN_THREADS / 32; ++wv) s += red[wv][threadIdx.x];
+    logits[(size_t)r * n_out + threadIdx.x] = s;
+  }
+}
+
+// dfeat[r][k] = sum_j dlogits[r][j] w[j][k]
+__global__ void linear_bwd_data_kernel(const float* __restrict__ dlogits, const float* __restrict__ w,
+                                       float* __restrict__ dfeat, long long rows, int k, int n_out) {
+  long long total = rows * k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / k;
+    int kk = (int)(i % k);
+    float s = 0.f;
+    for (int j = 0; j < n_out; ++j) s = fmaf(dlogits[r * n_out + j], w[(size_t)j * k + kk], s);
+    dfeat[i] = s;
+  }
+}
+
+// dw[j][k] (+)= sum_r dlogits[r][j] feat[r][k]  (thread per (j,k), rows in order -> deterministic)
+__global__ void linear_bwd_weight_kernel(const float* __restrict__ dlogits, const float* __restrict__ feat,
+                                         float* __restrict__ dw, float* __restrict__ db, int rows, int k, int n_out,
+                                         int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k * n_out) {
+    int j = i / k, kk = i % k;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s = fmaf(dlogits[(size_t)r * n_out + j], feat[(size_t)r * k + kk], s);
+    dw[i] = accumulate ? dw[i] + s : s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n_out && db) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += dlogits[(size_t)r * n_out + threadIdx.x];
+    db[threadIdx.x] = accumulate ? db[threadIdx.x] + s : s;
+  }
+}
+
+// ---- BCEWithLogits (mean) + gradient: n is tiny (2 per sequence), one CTA ---------------------------------
+__global__ void bce_with_logits_kernel(const float* __restrict__ z, const float* __restrict__ t, float* __restrict__ loss,
+                                       float* __restrict__ dz, int n, float grad_scale) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const float inv_n = 1.f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float zi = z[i], ti = t[i];
+    // max(z,0) - z*t + log1p(exp(-|z|))  (the numerically stable form torch uses)
+    s += fmaxf(zi, 0.f) - zi * ti + log1pf(expf(-fabsf(zi)));
+    if (dz) dz[i] = grad_scale * (1.f / (1.f + expf(-zi)) - ti) * inv_n;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    if (loss) loss[0] = tot * inv_n;
+  }
+}
+
+int launch_bce(const float* z, const float* t, float* loss, float* dz, int n, float grad_scale, cudaStream_t st) {
+  if (n == 0) return DARDS_OK;
+  bce_with_logits_kernel<<<1, 256, 0, st>>>(z, t, loss, dz, n, grad_scale);
+  DARDS_CHECK_LAUNCH("bce_with_logits");
+  return DARDS_OK;
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------
+static int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  if (b > 148LL * 16) b = 148LL * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int launch_avgpool2(int bwd, const void* src, void* dst, int n_breaths, int l_in, int c, int src_stride, int dst_stride,
+                    int dtype, cudaStream_t st) {
+  DARDS_CHECK_ARG(l_in % 2 == 0 && c % 4 == 0 && src_stride % 4 == 0 && dst_stride % 4 == 0,
+                  "avgpool2: L must be even, channels/strides multiples of 4");
+  long long rows_out = (long long)n_breaths * (l_in / 2);
+  if (rows_out == 0) return DARDS_OK;
+  int blocks = grid_for(rows_out * (c / 4), 256);
+  DARDS_DISPATCH_DTYPE(dtype, {
+    if (!bwd)
+      avgpool2_fwd_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), rows_out,
+                                                     l_in / 2, c / 4, src_stride, dst_stride);
+    else
+      avgpool2_bwd_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(src), static_cast<T*>(dst), rows_out,
+                                                     l_in / 2, c / 4, src_stride, dst_stride);
+  })
+  DARDS_CHECK_LAUNCH("avgpool2");
+  return DARDS_OK;
+}
+
+int launch_avgpool_full_fwd(const void* in, float* feat, int n_breaths, int l, int c, int in_stride, int dtype,
+                            cudaStream_t st) {
+  DARDS_CHECK_ARG(c % 4 == 0 && in_stride % 4 == 0, "avgpool: channels/stride must be multiples of 4");
+  if (n_breaths == 0) return DARDS_OK;
+  int blocks = grid_for((long long)n_breaths * (c / 4), 256);
+  DARDS_DISPATCH_DTYPE(dtype, {
+    avgpool_full_fwd_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(in), feat, n_breaths, l, c / 4, in_stride);
+  })
+  DARDS_CHECK_LAUNCH("avgpool_full_fwd");
+  return DARDS_OK;
+}
+
+int launch_avgpool_full_bwd(const float* dfeat, void* din, int n_breaths, int l, int c, int din_stride, int dtype,
+                            cudaStream_t st) {
+  DARDS_CHECK_ARG(c % 4 == 0 && din_stride % 4 == 0, "avgpool: channels/stride must be multiples of 4");
+  if (n_breaths == 0) return DARDS_OK;
+  int blocks = grid_for((long long)n_breaths * l * (c / 4), 256);
+  DARDS_DISPATCH_DTYPE(dtype, {
+    avgpool_full_bwd_kernel<T><<<blocks, 256, 0, st>>>(dfeat, static_cast<T*>(din), n_breaths, l, c / 4, din_stride);
+  })
+  DARDS_CHECK_LAUNCH("avgpool_full_bwd");
+  return DARDS_OK;
+}
+
+int launch_dropout(void* x, int n_rows, int c, int stride, float p, unsigned long long seed,
+                   const unsigned long long* seed_off, int dtype, cudaStream_t st) {
+  DARDS_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
+  if (n_rows == 0 || p == 0.f) return DARDS_OK;
+  int blocks = grid_for((long long)n_rows * c, 256);
+  DARDS_DISPATCH_DTYPE(dtype, {
+    dropout_kernel<T><<<blocks, 256, 0, st>>>(static_cast<T*>(x), n_rows, c, stride, p, 1.f / (1.f - p), seed, seed_off);
+  })
+  DARDS_CHECK_LAUNCH("dropout");
+  return DARDS_OK;
+}
+
+int launch_linear_fwd(const float* feat, const float* w, const float* bias, float* logits, int rows, int k, int n_out,
+                      cudaStream_t st) {
+  DARDS_CHECK_ARG(n_out >= 1 && n_out <= LIN_MAX_OUT, "linear: n_out must be in [1,%d]", LIN_MAX_OUT);
+  if (rows == 0) return DARDS_OK;
+  linear_fwd_kernel<<<rows, LIN_THREADS, 0, st>>>(feat, w, bias, logits, k, n_out);
+  DARDS_CHECK_LAUNCH("linear_fwd");
+  return DARDS_OK;
+}
+
+int launch_linear_bwd(const float* dlogits, const float* feat, const float* w, float* dfeat, float* dw, float* db,
+                      int accumulate, int rows, int k, int n_out, cudaStream_t st) {
+  DARDS_CHECK_ARG(n_out >= 1 && n_out <= LIN_MAX_OUT, "linear: n_out must be in [1,%d]", LIN_MAX_OUT);
+  if (dfeat && rows > 0) {
+    linear_bwd_data_kernel<<<grid_for((long long)rows * k, 256), 256, 0, st>>>(dlogits, w, dfeat, rows, k, n_out);
+    DARDS_CHECK_LAUNCH("linear_bwd_data");
+  }
+  if (dw) {
+    linear_bwd_weight_kernel<<<ceil_div((long long)k * n_out, 256), 256, 0, st>>>(dlogits, feat, dw, db, rows, k, n_out,
+                                                                                 accumulate);
+    DARDS_CHECK_LAUNCH("linear_bwd_weight");
+  }
+  return DARDS_OK;
+}
+
+}  // namespace dards

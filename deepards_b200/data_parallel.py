@@ -1,0 +1,201 @@
+"""Data-parallel training step: one process per GPU, NCCL all-reduce of the flat gradient buffer.
+
+Replaces `nn.DataParallel(model).cuda()` (deepards/train_ards_detector.py:93-96), which the reference's author
+notes is effectively unusable (:198-203).  Semantics kept from that path:
+
+  * the batch is split on dim 0; every sequence's forward/backward (incl. its BatchNorm statistics) is independent
+    of every other sequence, so sharding is exact and the ONLY collective is the gradient all-reduce;
+  * the loss is the mean over the GLOBAL batch: each rank back-propagates its local mean and the reduced gradient
+    is scaled by 1/world_size;
+  * the reference's gradient clamp (`p.register_hook(clamp)`, :474-476) acts on the REDUCED gradient under
+    DataParallel, so here it is applied after the all-reduce, fused with the optimizer update
+    (SGD-Nesterov momentum 0.9 / Adam, :416-422) in one kernel over the flat buffers;
+  * parameters that never receive a gradient (ResNet's conv1_alt/conv2/bn2; frozen parameters) are left out of
+    the update, exactly like torch.optim skipping `p.grad is None`.
+
+The gradient buffer is reduced in buckets, last layers first, on a communication stream that waits on events
+recorded inside the backward pass, so the reduction of layer4's 11.5 MB overlaps the backward of layers 1-3.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib, engine
+
+
+def param_layout(net):
+    """[(name, param, offset)] and total length of the flat fp32 buffers (16-byte aligned slots)."""
+    out, off = [], 0
+    for n, p in net.named_parameters():
+        out.append((n, p, off))
+        off += (p.numel() + 3) // 4 * 4
+    return out, off
+
+
+def shard_bounds(batch, world, rank):
+    """[begin, end) of this rank's sequences: contiguous, remainder to the first ranks."""
+    base, rem = divmod(batch, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def live_ranges(layout, live_ids):
+    """Merge the flat slots of the parameters in `live_ids` into maximal contiguous [begin, end) ranges."""
+    ranges = []
+    for _, p, off in layout:
+        if id(p) not in live_ids:
+            continue
+        end = off + (p.numel() + 3) // 4 * 4
+        if ranges and ranges[-1][1] == off:
+            ranges[-1][1] = end
+        else:
+            ranges.append([off, end])
+    return [tuple(r) for r in ranges]
+
+
+def make_buckets(total, cut_points, min_elems):
+    """Split [0, total) at the given candidate offsets (descending readiness order: a suffix of the buffer is
+    complete first) into buckets of at least `min_elems`, returned last-first."""
+    cuts = sorted(set(c for c in cut_points if 0 < c < total), reverse=True)
+    buckets, end = [], total
+    for c in cuts:
+        if end - c >= min_elems:
+            buckets.append((c, end))
+            end = c
+    if end > 0:
+        buckets.append((0, end))
+    return buckets
+
+
+class BucketedAllReduce(object):
+    """Sum-all-reduce of slices of one flat tensor, issued asynchronously per bucket."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.handles = []
+
+    def reduce(self, flat, begin, end):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self.handles.append(dist.all_reduce(flat[begin:end], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self):
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+
+
+class DataParallelTrainer(object):
+    def __init__(self, net, lr=1e-3, optimizer="sgd", momentum=0.9, weight_decay=1e-4, clip_val=0.01, group=None,
+                 bucket_mb=4.0):
+        if optimizer not in ("sgd", "adam"):
+            raise ValueError("optimizer must be 'sgd' or 'adam'")
+        self.net, self.lr, self.optimizer = net, lr, optimizer
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.clip = float(clip_val) if clip_val else 0.0
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.step_count = 0
+        self._flatten()
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self.reducer = BucketedAllReduce(group)
+        self.loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    # ---- flat parameter / optimizer-state buffers (same slot table as Plan.grad_flat) ----------------------
+    def _flatten(self):
+        layout, total = param_layout(self.net)
+        p0 = layout[0][1]
+        self.device = p0.device
+        if self.device.type != "cuda":
+            raise RuntimeError("DataParallelTrainer needs the network on a CUDA device")
+        flat = torch.zeros(max(total, 4), dtype=torch.float32, device=self.device)
+        for _, p, off in layout:
+            flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + p.numel()].view(p.shape)
+        self.layout, self.total, self.param_flat = layout, total, flat
+        self.state1 = torch.zeros_like(flat)
+        self.state2 = torch.zeros_like(flat) if self.optimizer == "adam" else None
+        if self.world > 1:
+            dist.broadcast(self.param_flat, src=0, group=self.group)  # DataParallel broadcasts device-0 weights
+
+    def plan_for(self, x):
+        net = self.net
+        bb = net.breath_block
+        from .torch_cnn_linear_network import CNNSingleBreathLinearNetwork, _drop_key
+        mode = "per_breath" if isinstance(net, CNNSingleBreathLinearNetwork) else "cnn_linear"
+        n = x.numel() // engine.SEQ_LEN
+        training = bb.training
+        from .autograd import module_precision
+        plan = engine.get_plan(net, bb, net.linear_final, n, x.shape[1], module_precision(net), mode,
+                               dropout=_drop_key(bb) if training else (), update_running=training)
+        if getattr(plan, "_dp_ranges", None) is None:
+            live = set(i for i in plan.grad_written
+                       if any(id(p) == i and p.requires_grad for _, p, _ in self.layout))
+            plan._dp_ranges = live_ranges(self.layout, live)
+            plan._dp_buckets = make_buckets(self.total, [off for off, _ in plan.bwd_marks], self.bucket_elems)
+        return plan
+
+    def train_step(self, x, target):
+        """x: this rank's (B_local, 20, 1, 224) on the device, target (B_local, 2).  Returns the device tensor
+        holding the local mean loss (no host synchronisation)."""
+        plan = self.plan_for(x)
+        st = plan._stream()
+        plan.load_input(x)
+        plan.run_forward()
+        t = target if target.dtype == torch.float32 else target.float()
+        _lib.call("dards_bce_with_logits", plan.logits.data_ptr(), t.contiguous().data_ptr(), self.loss_buf.data_ptr(),
+                  plan.dlogits.data_ptr(), plan.logits.numel(), 1.0, st)
+        if self.world > 1:
+            self._backward_overlapped(plan)
+        else:
+            plan.run_backward()
+        self._update(plan, st)
+        return self.loss_buf
+
+    def _backward_overlapped(self, plan):
+        """Replay the backward in segments; after each segment the comm stream reduces the buckets that became
+        complete.  Buckets are suffixes of the flat buffer (backward finishes the last layers first)."""
+        if plan.bwd_serial + 1 != plan.fwd_serial:
+            raise RuntimeError("backward() without a matching forward()")
+        cur = torch.cuda.current_stream(self.device)
+        st = cur.cuda_stream
+        marks = dict((idx, off) for off, idx in plan.bwd_marks)  # call index -> offset complete from there on
+        pending = list(plan._dp_buckets)
+        calls = plan.bwd.calls
+        for i, (name, f, args) in enumerate(calls):
+            rc = f(*args, st)
+            if rc != 0:
+                _lib.check(rc, name)
+            done_from = marks.get(i + 1)
+            if done_from is not None and pending and pending[0][0] >= done_from:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.comm_stream.wait_event(ev)
+                with torch.cuda.stream(self.comm_stream):
+                    while pending and pending[0][0] >= done_from:
+                        b, e = pending.pop(0)
+                        self.reducer.reduce(plan.grad_flat, b, e)
+        if pending:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                for b, e in pending:
+                    self.reducer.reduce(plan.grad_flat, b, e)
+        plan.bwd_serial = plan.fwd_serial
+        self.reducer.wait()
+        cur.wait_stream(self.comm_stream)
+
+    def _update(self, plan, st):
+        self.step_count += 1
+        scale = 1.0 / self.world
+        g, p = plan.grad_flat.data_ptr(), self.param_flat.data_ptr()
+        for b, e in plan._dp_ranges:
+            if self.optimizer == "sgd":
+                _lib.call("dards_clamp_sgd_nesterov", p + 4 * b, g + 4 * b, self.state1.data_ptr() + 4 * b, e - b, self.lr,
+                          self.momentum, self.weight_decay, self.clip, scale, 1 if self.step_count == 1 else 0, st)
+            else:
+                _lib.call("dards_clamp_adam", p + 4 * b, g + 4 * b, self.state1.data_ptr() + 4 * b,
+                          self.state2.data_ptr() + 4 * b, e - b, self.lr, 0.9, 0.999, 1e-8, self.clip, scale,
+                          self.step_count, st)
+        plan._packed_version = None  # weights changed behind autograd's back: repack before the next forward

@@ -1,0 +1,69 @@
+"""cnn_linear heads on the B200 backend -- drop-in for deepards/models/torch_cnn_linear_network.py.
+
+`CNNLinearNetwork(breath_block, sequence_size, metadata_features)` (torch_cnn_linear_network.py:92-113) and
+`CNNSingleBreathLinearNetwork(breath_block)` (:49-67): same attributes (`breath_block`, `linear_final`,
+`seq_size`), same `forward(x, metadata)` contract and error for a wrong window length.
+
+Where the reference loops over the batch in Python and calls the backbone once per 20-breath sequence (so that
+BatchNorm sees one sequence at a time), this implementation runs ALL B*20 breaths through one kernel plan whose
+BatchNorm kernels take their statistics per group of 20 consecutive breaths -- same numbers, one launch
+sequence, no O(B^2) torch.cat.
+"""
+import torch.nn as nn
+
+from . import autograd as _ag
+from .resnet import _Picklable
+
+
+def _drop_key(backbone):
+    feats = getattr(backbone, "features", None)
+    return feats._drop_key() if feats is not None and hasattr(feats, "_drop_key") else ()
+
+
+class _HeadBase(_Picklable, nn.Module):
+    def _check(self, x):
+        # input should be in shape: (batches, breaths in seq, chans, 224)
+        if x.shape[-1] != 224:
+            raise Exception('input breaths must have sequence length of 224')
+        if x.dim() != 4 or x.shape[2] != 1:
+            raise NotImplementedError("deepards_b200 heads take (B, breaths, 1, 224) inputs, got %s" % (tuple(x.shape),))
+        if not hasattr(self.breath_block, "network_name") or not hasattr(self.breath_block, "precision"):
+            raise TypeError("breath_block must be a deepards_b200 backbone (resnet18 / densenet18 from this package)")
+
+    @property
+    def precision(self):
+        return self.breath_block.precision
+
+    @precision.setter
+    def precision(self, value):
+        self.breath_block.precision = value
+
+
+class CNNLinearNetwork(_HeadBase):
+    """Flatten the 20 x F features of each sequence and classify it with one Linear layer."""
+
+    def __init__(self, breath_block, sequence_size, metadata_features):
+        super(CNNLinearNetwork, self).__init__()
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.linear_final = nn.Linear(self.breath_block.n_out_filters * sequence_size + metadata_features, 2)
+
+    def forward(self, x, metadata=None):
+        self._check(x)
+        return _ag.run_plan(self, self.breath_block, self.linear_final, x, x.shape[1], "cnn_linear",
+                            _drop_key(self.breath_block))
+
+
+class CNNSingleBreathLinearNetwork(_HeadBase):
+    """One prediction per breath: Linear(F, 2) on every breath's pooled features -> (B, breaths, 2)."""
+
+    def __init__(self, breath_block):
+        super(CNNSingleBreathLinearNetwork, self).__init__()
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.linear_final = nn.Linear(self.breath_block.n_out_filters, 2)
+
+    def forward(self, x, metadata=None):
+        self._check(x)
+        return _ag.run_plan(self, self.breath_block, self.linear_final, x, x.shape[1], "per_breath",
+                            _drop_key(self.breath_block))

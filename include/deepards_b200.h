@@ -1,0 +1,180 @@
+/*
+ * deepards_b200 -- C ABI of the B200 (sm_100a) backend for the deepards cnn_linear hot path.
+ *
+ * The reference (hahnicity/deepards) has NO native interface: its extension points are two
+ * Python dicts, `base_networks` (deepards/train_ards_detector.py:45-69) and `network_map`
+ * (deepards/train_ards_detector.py:1410-1436), and all arithmetic is torch.nn library calls.
+ * This header is therefore the boundary that the replacement Python modules
+ * (deepards_b200/resnet.py, densenet.py, torch_cnn_linear_network.py -- same names, ctor
+ * signatures and state_dict keys as deepards/models/*) bind with ctypes; every entry point
+ * cites the torch.nn call site in the reference that it replaces.
+ *
+ * Conventions
+ *  - Plain C symbols, raw DEVICE pointers, int sizes, a dtype enum and a cudaStream_t passed
+ *    as void*.  No torch types.  All buffers are owned by the caller (PyTorch's caching
+ *    allocator); the library never allocates, frees or retains device memory.
+ *  - Every function only ENQUEUES work on `stream` and returns; no implicit synchronisation.
+ *  - Return value: DARDS_OK (0) or a negative dards_status; dards_last_error() gives the
+ *    message of the last failure on the calling thread.  Nothing throws or aborts.
+ *  - Activation layout: channels-last.  A tensor the reference holds as (N, C, L) lives here
+ *    as (N, L, C) with a row stride `*_stride` >= C (in elements), so that a channel slice
+ *    of a wider buffer (DenseNet concatenation, densenet.py:40) is addressable in place.
+ *    `dtype` is the storage type of ACTIVATIONS and packed weights (fp32 or bf16); all
+ *    accumulation, BatchNorm statistics, parameters and parameter gradients are fp32.
+ *  - "group": BatchNorm statistics are taken over `group` consecutive breaths (20 = one
+ *    sequence; deepards/models/torch_cnn_linear_network.py:104-113 calls the backbone once
+ *    per sequence), i.e. over group*L rows per channel.
+ */
+#ifndef DEEPARDS_B200_H_
+#define DEEPARDS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dards_status {
+  DARDS_OK = 0,
+  DARDS_ERR_INVALID_ARGUMENT = -1,
+  DARDS_ERR_CUDA = -2,
+  DARDS_ERR_UNSUPPORTED = -3
+} dards_status;
+
+typedef enum dards_dtype { DARDS_F32 = 0, DARDS_BF16 = 1 } dards_dtype;
+
+/* ---- library ---------------------------------------------------------------------- */
+int dards_version(void);                 /* ABI version, bumped on any signature change */
+const char* dards_last_error(void);      /* thread-local, never NULL */
+/* 1 if the device behind the current context is compute capability 10.x (B200). */
+int dards_device_supported(void);
+
+/* ---- weights ---------------------------------------------------------------------- */
+/* nn.Conv1d weight (Cout, Cin, K) fp32 [resnet.py:7,88,128; densenet.py:25,30,75,119] ->
+ * the two packed forms the kernels read, in `dtype`:
+ *   w_kio[t][ci][co]  (reduction over ci, outputs co contiguous)
+ *   w_koi[t][co][ci]  (reduction over co, outputs ci contiguous)
+ * either output pointer may be NULL. */
+int dards_pack_conv_weight(const float* w, void* w_kio, void* w_koi, int c_out, int c_in, int ktaps,
+                           int dtype, void* stream);
+
+/* ---- convolution (nn.Conv1d, bias=False) ------------------------------------------ */
+/* Forward: out[n,q,co] = sum_{t,ci} in[n, q*stride + t - pad, ci] * W[co,ci,t]  (+ addend[n,q,co]).
+ * `w_packed`: w_kio for impl 0, w_koi for impl 1 (the MMA wants the reduction dim contiguous);
+ * `addend` may be NULL.  Replaces nn.Conv1d.forward
+ * at resnet.py:27,31,35 and densenet.py:25,30,75 (the stem conv has its own entry point).
+ * impl: 0 = CUDA-core fp32-accumulate implicit GEMM (any dtype), 1 = tcgen05 (bf16 only). */
+int dards_conv1d_fwd(const void* in, const void* w_packed, void* out, const void* addend, int n_breaths, int l_in,
+                     int l_out, int c_in, int c_out, int in_stride, int out_stride, int addend_stride, int ktaps,
+                     int stride, int pad, int dtype, int impl, void* stream);
+
+/* Data gradient: din[n,p,ci] = sum_{t,co} dout[n,q,co] * W[co,ci,t] over all (q,t) with
+ * q*stride + t - pad == p  (+ addend).  `w_packed`: w_koi for impl 0, w_kio for impl 1.
+ * autograd of the calls above. */
+int dards_conv1d_dgrad(const void* dout, const void* w_packed, void* din, const void* addend, int n_breaths,
+                       int l_in, int l_out, int c_in, int c_out, int dout_stride, int din_stride,
+                       int addend_stride, int ktaps, int stride, int pad, int dtype, int impl, void* stream);
+
+/* Weight gradient: dW[co,ci,t] (+)= sum_{n,q} dout[n,q,co] * in[n, q*stride + t - pad, ci], fp32,
+ * written in the parameter's own (Cout, Cin, K) layout.  Deterministic: split-K partial sums go to
+ * `workspace` (dards_conv1d_wgrad_workspace_bytes) and are reduced in a fixed order. */
+int dards_conv1d_wgrad(const void* in, const void* dout, float* dw, int accumulate, void* workspace,
+                       long long workspace_bytes, int n_breaths, int l_in, int l_out, int c_in, int c_out,
+                       int in_stride, int dout_stride, int ktaps, int stride, int pad, int dtype, int impl,
+                       void* stream);
+long long dards_conv1d_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps, int impl);
+
+/* ---- grouped BatchNorm1d (+ residual add, + ReLU) ---------------------------------- */
+/* Training-mode nn.BatchNorm1d over groups of `rows_per_group` = group*L rows: biased variance, eps;
+ * out = [relu]( (x-mean)*rstd*gamma + beta [+ res] ).  Saves mean/rstd as [n_groups][C] fp32.
+ * Replaces bn/relu/"out += residual" at resnet.py:28-29,32,37-38,146-153 and norm/relu at
+ * densenet.py:23-24,28-29,73-74,121-122,149,182.  x and out may alias. */
+int dards_gbn_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta,
+                  float* save_mean, float* save_rstd, int n_groups, int rows_per_group, int c, int x_stride,
+                  int out_stride, int res_stride, float eps, int relu, int dtype, void* stream);
+
+/* Backward of the above.  g = dout * relu_mask; dx (+)= gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)).
+ * relu_mode: 0 none, 1 recompute mask from x (xhat*gamma+beta > 0), 2 mask = (mask_src > 0).
+ * dres (optional) receives g (gradient of the residual branch).  Per-group partial sums
+ * dgamma_part/dbeta_part [n_groups][C] are reduced with dards_reduce_rows. */
+int dards_gbn_bwd(const void* dout, const void* x, const void* mask_src, const float* gamma, const float* beta,
+                  const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
+                  float* dgamma_part, float* dbeta_part, int n_groups, int rows_per_group, int c,
+                  int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode,
+                  int dtype, void* stream);
+
+/* out[c] (+)= sum_r part[r][c]   (fixed order -> deterministic) */
+int dards_reduce_rows(const float* part, float* out, int rows, int c, int accumulate, void* stream);
+
+/* nn.BatchNorm1d running statistics, updated once per group IN ORDER (momentum, unbiased variance;
+ * SURVEY.md hard part 6); num_batches_tracked (int64) += n_groups. */
+int dards_bn_running_update(const float* save_mean, const float* save_rstd, float* running_mean,
+                            float* running_var, long long* num_batches_tracked, int n_groups,
+                            int rows_per_group, int c, float momentum, float eps, void* stream);
+
+/* ---- stem: Conv1d(1->C0,k7,s2,p3) + BN + ReLU + Max/AvgPool1d(3,2,1) ---------------- */
+/* resnet.py:143-153 / densenet.py:119-123 fused: x (N,224) fp32 -> out (N,56,C0).  Nothing but the
+ * group statistics is saved; the backward recomputes the convolution from x. pool: 0 max, 1 avg. */
+int dards_stem_fwd(const float* x, const float* w, const float* gamma, const float* beta, void* out,
+                   float* save_mean, float* save_rstd, int n_groups, int group, int c0, int out_stride,
+                   float eps, int pool, int dtype, void* stream);
+/* dout (N,56,C0) -> per-group partials dw_part [n_groups][C0][7], dgamma_part/dbeta_part [n_groups][C0]. */
+int dards_stem_bwd(const void* dout, const float* x, const float* w, const float* gamma, const float* beta,
+                   const float* save_mean, const float* save_rstd, float* dw_part, float* dgamma_part,
+                   float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, int dtype,
+                   void* stream);
+
+/* ---- pooling, dropout --------------------------------------------------------------- */
+/* nn.AvgPool1d(2,2) (densenet.py:77): (N,L,C) -> (N,L/2,C) and its backward. */
+int dards_avgpool2_fwd(const void* in, void* out, int n_breaths, int l_in, int c, int in_stride, int out_stride,
+                       int dtype, void* stream);
+int dards_avgpool2_bwd(const void* dout, void* din, int n_breaths, int l_in, int c, int dout_stride,
+                       int din_stride, int dtype, void* stream);
+/* nn.AvgPool1d(7) + flatten (resnet.py:160-161, densenet.py:183-184): (N,7,C) -> feat (N,C) fp32. */
+int dards_avgpool_full_fwd(const void* in, float* feat, int n_breaths, int l, int c, int in_stride, int dtype,
+                           void* stream);
+int dards_avgpool_full_bwd(const float* dfeat, void* din, int n_breaths, int l, int c, int din_stride, int dtype,
+                           void* stream);
+/* F.dropout(p, training=True) (densenet.py:37-39) in place on a channel slice; the mask is a pure
+ * function of (seed, element index) so the backward regenerates it. */
+int dards_dropout(void* x, int n_rows, int c, int stride, float p, unsigned long long seed,
+                  const unsigned long long* seed_offset_dev /* nullable: added to seed on the device, so a
+                  captured CUDA graph draws a fresh mask on every replay */,
+                  int dtype, void* stream);
+
+/* ---- linear head --------------------------------------------------------------------- */
+/* nn.Linear(K,2) on flattened features (torch_cnn_linear_network.py:102,110 and :55,63):
+ * logits[r][j] = bias[j] + sum_k feat[r][k] * w[j][k], rows r = sequences (K = 20*F) or breaths (K = F). */
+int dards_linear_fwd(const float* feat, const float* w, const float* bias, float* logits, int rows, int k,
+                     int n_out, void* stream);
+/* dfeat[r][k] = sum_j dlogits[r][j] w[j][k];  dw[j][k] (+)= sum_r dlogits[r][j] feat[r][k];  db[j] (+)= sum_r ... */
+int dards_linear_bwd(const float* dlogits, const float* feat, const float* w, float* dfeat, float* dw, float* db,
+                     int accumulate, int rows, int k, int n_out, void* stream);
+
+/* torch.nn.BCEWithLogitsLoss() (train_ards_detector.py:530, 929-930), mean over n elements:
+ * loss[0] = mean(softplus(z) - t*z);  dlogits = grad_scale * (sigmoid(z) - t) / n.  One CTA. */
+int dards_bce_with_logits(const float* logits, const float* target, float* loss, float* dlogits, int n,
+                          float grad_scale, void* stream);
+
+/* ---- optimizer (after the gradient all-reduce) ---------------------------------------- */
+/* g = clamp(grad*grad_scale, -clip, +clip) [clip<=0: no clamp]  (train_ards_detector.py:474-476, applied
+ * AFTER the reduction like nn.DataParallel does -- SURVEY.md 8e); then torch.optim.SGD(momentum,
+ * weight_decay, nesterov=True) (train_ards_detector.py:421) on flat fp32 buffers.
+ * first_step != 0: momentum buffer is initialised with the gradient (torch semantics). */
+int dards_clamp_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr,
+                             float momentum, float weight_decay, float clip, float grad_scale, int first_step,
+                             void* stream);
+/* torch.optim.Adam(lr) defaults (train_ards_detector.py:419): betas (0.9,0.999), eps 1e-8. step is 1-based. */
+int dards_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                     float beta1, float beta2, float eps, float clip, float grad_scale, int step, void* stream);
+
+/* ---- debugging ----------------------------------------------------------------------- */
+/* Overrides one field of the tcgen05 shared-memory / instruction descriptors (key: 0 = LBO field,
+ * 1 = version field, 2 = SBO field for K-major tiles; value < 0 restores the default).  Only the
+ * descriptor unit tests use it. */
+int dards_tc_debug_set(int key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPARDS_B200_H_ */

@@ -1,0 +1,312 @@
+"""GPU: every C-ABI kernel against the same operation done by PyTorch in fp32 (and, for bf16 storage,
+against PyTorch on the bf16-rounded inputs).  Tolerances are written next to each check.
+
+These are the per-kernel parity tests; tests/test_model_parity_gpu.py checks whole networks against the oracle
+and the golden vectors recorded from the reference.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from tests.helpers import rel_err  # noqa: E402
+
+
+def K():
+    from deepards_b200 import kernels
+    return kernels
+
+
+def cl(x):  # (N, C, L) -> channels-last (N, L, C)
+    return x.permute(0, 2, 1).contiguous()
+
+
+def ncl(x):
+    return x.permute(0, 2, 1).contiguous()
+
+
+DEV = "cuda"
+
+CONV_CASES = [
+    # n, cin, cout, l, k, stride, pad
+    (40, 64, 64, 56, 3, 1, 1),
+    (40, 64, 128, 56, 3, 2, 1),
+    (40, 64, 128, 56, 1, 2, 0),
+    (20, 128, 128, 28, 3, 1, 1),
+    (23, 256, 512, 14, 3, 2, 1),   # ragged number of breaths
+    (33, 512, 512, 7, 3, 1, 1),
+    (20, 96, 128, 28, 1, 1, 0),    # DenseNet conv1 (Cin = 96)
+    (20, 128, 32, 14, 3, 1, 1),    # DenseNet conv2 (Cout = 32)
+    (20, 16, 32, 56, 3, 2, 1),     # 16-plane ResNet
+    (4, 64, 64, 224, 7, 2, 3),     # generic 7-tap
+]
+
+
+def _conv_inputs(case, seed=0):
+    n, cin, cout, l, k, s, p = case
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(n, cin, l, generator=g).to(DEV)
+    w = (torch.randn(cout, cin, k, generator=g) / (cin * k) ** 0.5).to(DEV)
+    lo = (l + 2 * p - k) // s + 1
+    dy = torch.randn(n, cout, lo, generator=g).to(DEV)
+    return x, w, dy
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32(case):
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case)
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    y_ref = F.conv1d(x, w, stride=s, padding=p)
+    dx_ref, dw_ref = torch.autograd.grad(y_ref, [x, w], dy)
+    y = K().conv1d_fwd(cl(x.detach()), w.detach(), s, p, impl=0)
+    assert rel_err(ncl(y), y_ref) < 2e-5
+    dx = K().conv1d_dgrad(cl(dy), w.detach(), l, s, p, impl=0)
+    assert rel_err(ncl(dx), dx_ref) < 2e-5
+    dw = K().conv1d_wgrad(cl(x.detach()), cl(dy), k, s, p, impl=0)
+    assert rel_err(dw, dw_ref) < 5e-5
+
+
+def test_conv_simt_strided_views_and_addend():
+    """channel slices of wider buffers (DenseNet concat) and the fused `+ addend` epilogue."""
+    case = (20, 64, 32, 28, 3, 1, 1)
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 3)
+    wide_in = torch.randn(n, l, 128, device=DEV)
+    wide_in[:, :, :cin] = cl(x)
+    wide_out = torch.zeros(n, l, 128, device=DEV)
+    add = torch.randn(n, l, cout, device=DEV)
+    K().conv1d_fwd(wide_in[:, :, :cin], w, s, p, impl=0, out=wide_out[:, :, 96:128], addend=add)
+    ref = cl(F.conv1d(x, w, stride=s, padding=p)) + add
+    assert rel_err(wide_out[:, :, 96:128], ref) < 2e-5
+    assert float(wide_out[:, :, :96].abs().max()) == 0.0  # nothing outside the slice was touched
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:8])
+def test_conv_simt_bf16_storage(case):
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 1)
+    xb, wb, dyb = x.bfloat16(), w.bfloat16(), dy.bfloat16()
+    xr = xb.float().requires_grad_(True)
+    wr = wb.float().requires_grad_(True)
+    y_ref = F.conv1d(xr, wr, stride=s, padding=p)
+    dx_ref, dw_ref = torch.autograd.grad(y_ref, [xr, wr], dyb.float())
+    # bf16 output rounding: 2^-8 relative per element
+    y = K().conv1d_fwd(cl(xb), w, s, p, impl=0)
+    assert rel_err(ncl(y).float(), y_ref) < 6e-3
+    dx = K().conv1d_dgrad(cl(dyb), w, l, s, p, impl=0)
+    assert rel_err(ncl(dx).float(), dx_ref) < 6e-3
+    dw = K().conv1d_wgrad(cl(xb), cl(dyb), k, s, p, impl=0)  # fp32 output, bf16-rounded weights not involved
+    assert rel_err(dw, dw_ref) < 1e-4
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:9])
+def test_conv_tcgen05_forward(case):
+    """tcgen05/TMEM/TMA implicit GEMM == CUDA-core kernel on identical bf16 operands (fp32 accumulation both)."""
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 2)
+    xb = cl(x.bfloat16())
+    y_simt = K().conv1d_fwd(xb, w, s, p, impl=0)
+    y_tc = K().conv1d_fwd(xb, w, s, p, impl=1)
+    torch.cuda.synchronize()
+    # both round the same fp32 sums (different summation order) to bf16: at most one bf16 ulp apart
+    assert rel_err(y_tc.float(), y_simt.float()) < 8e-3
+    ref = cl(F.conv1d(xb.permute(0, 2, 1).float(), w.bfloat16().float(), stride=s, padding=p))
+    assert rel_err(y_tc.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES[:9] if c[5] == 1])
+def test_conv_tcgen05_dgrad(case):
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 4)
+    dyb = cl(dy.bfloat16())
+    add = torch.randn(n, l, cin, device=DEV).bfloat16()
+    d_simt = K().conv1d_dgrad(dyb, w, l, s, p, impl=0, addend=add)
+    d_tc = K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add)
+    torch.cuda.synchronize()
+    assert rel_err(d_tc.float(), d_simt.float()) < 8e-3
+
+
+def test_conv_tcgen05_into_channel_slice():
+    case = (20, 128, 32, 14, 3, 1, 1)
+    n, cin, cout, l, k, s, p = case
+    x, w, _ = _conv_inputs(case, 5)
+    xb = cl(x.bfloat16())
+    wide = torch.zeros(n, l, 128, device=DEV, dtype=torch.bfloat16)
+    K().conv1d_fwd(xb, w, s, p, impl=1, out=wide[:, :, 64:96])
+    ref = K().conv1d_fwd(xb, w, s, p, impl=0)
+    torch.cuda.synchronize()
+    assert rel_err(wide[:, :, 64:96].float(), ref.float()) < 8e-3
+    assert float(wide[:, :, :64].abs().max()) == 0.0 and float(wide[:, :, 96:].abs().max()) == 0.0
+
+
+def _bn_ref(x, gamma, beta, group, relu, res=None):
+    """x (N, C, L); per-group training-mode batch norm with autograd."""
+    outs = []
+    for i in range(0, x.shape[0], group):
+        y = F.batch_norm(x[i:i + group], None, None, gamma, beta, True, 0.0, 1e-5)
+        outs.append(y)
+    y = torch.cat(outs)
+    if res is not None:
+        y = y + res
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("n,c,l,group", [(40, 64, 56, 20), (60, 128, 7, 20), (24, 16, 28, 8), (20, 96, 14, 20)])
+@pytest.mark.parametrize("variant", ["relu", "plain", "res_relu"])
+def test_gbn_forward_backward_fp32(n, c, l, group, variant):
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(n, c, l, generator=g) * 2 + 0.5).to(DEV).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(c, generator=g)).to(DEV).requires_grad_(True)
+    beta = (0.2 * torch.randn(c, generator=g)).to(DEV).requires_grad_(True)
+    res = torch.randn(n, c, l, generator=g).to(DEV).requires_grad_(True) if variant == "res_relu" else None
+    dy = torch.randn(n, c, l, generator=g).to(DEV)
+    relu = variant != "plain"
+    y_ref = _bn_ref(x, gamma, beta, group, relu, res)
+    ins = [x, gamma, beta] + ([res] if res is not None else [])
+    grads = torch.autograd.grad(y_ref, ins, dy)
+    out, mean, rstd = K().gbn_fwd(cl(x.detach()), gamma.detach(), beta.detach(), group * l, relu,
+                                  res=cl(res.detach()) if res is not None else None)
+    assert rel_err(ncl(out), y_ref) < 1e-5
+    mode = 0 if variant == "plain" else (1 if variant == "relu" else 2)
+    dx, dgamma, dbeta, dres = K().gbn_bwd(cl(dy), cl(x.detach()), gamma.detach(), beta.detach(), mean, rstd, group * l,
+                                          mode, mask_src=out if mode == 2 else None, want_dres=res is not None)
+    assert rel_err(ncl(dx), grads[0]) < 2e-5
+    assert rel_err(dgamma, grads[1]) < 2e-5
+    assert rel_err(dbeta, grads[2]) < 2e-5
+    if res is not None:
+        assert rel_err(ncl(dres), grads[3]) < 1e-6
+
+
+def test_gbn_bf16_storage():
+    n, c, l, group = 40, 64, 28, 20
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(n, c, l, generator=g).to(DEV).bfloat16()
+    gamma = (1 + 0.2 * torch.randn(c, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(c, generator=g)).to(DEV)
+    y_ref = _bn_ref(x.float(), gamma, beta, group, True)
+    out, mean, rstd = K().gbn_fwd(cl(x), gamma, beta, group * l, True)
+    assert out.dtype == torch.bfloat16
+    assert rel_err(ncl(out).float(), y_ref) < 6e-3
+
+
+def test_bn_running_update_matches_sequential_torch():
+    from deepards_b200 import _lib
+    n, c, l, group = 60, 32, 14, 20
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, c, l, generator=g).to(DEV)
+    bn = torch.nn.BatchNorm1d(c).to(DEV).train()
+    for i in range(0, n, group):
+        bn(x[i:i + group])
+    gamma, beta = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    _, mean, rstd = K().gbn_fwd(cl(x), gamma, beta, group * l, False)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    _lib.call("dards_bn_running_update", mean.data_ptr(), rstd.data_ptr(), rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(),
+              n // group, group * l, c, 0.1, 1e-5, torch.cuda.current_stream().cuda_stream)
+    assert rel_err(rm, bn.running_mean) < 1e-5
+    assert rel_err(rv, bn.running_var) < 1e-5
+    assert int(nbt) == 3
+
+
+@pytest.mark.parametrize("c0,group,pool", [(64, 20, 0), (16, 20, 0), (64, 20, 1), (32, 7, 0), (64, 60, 0)])
+def test_stem_forward_backward(c0, group, pool):
+    n = group * 3
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(n, 1, 224, generator=g).to(DEV)
+    w = (torch.randn(c0, 1, 7, generator=g) * 0.3).to(DEV).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(c0, generator=g)).to(DEV).requires_grad_(True)
+    beta = (0.2 * torch.randn(c0, generator=g)).to(DEV).requires_grad_(True)
+    dy = torch.randn(n, c0, 56, generator=g).to(DEV)
+    outs = []
+    for i in range(0, n, group):
+        y = F.conv1d(x[i:i + group], w, stride=2, padding=3)
+        y = F.relu(F.batch_norm(y, None, None, gamma, beta, True, 0.0, 1e-5))
+        y = F.max_pool1d(y, 3, 2, 1) if pool == 0 else F.avg_pool1d(y, 3, 2, 1)
+        outs.append(y)
+    y_ref = torch.cat(outs)
+    gw, gg, gb = torch.autograd.grad(y_ref, [w, gamma, beta], dy)
+    out, mean, rstd = K().stem_fwd(x.view(n, 224), w.detach(), gamma.detach(), beta.detach(), group, pool, torch.float32)
+    assert rel_err(ncl(out), y_ref) < 1e-5
+    dw, dgamma, dbeta = K().stem_bwd(cl(dy), x.view(n, 224), w.detach(), gamma.detach(), beta.detach(), mean, rstd, group,
+                                     pool)
+    assert rel_err(dw, gw) < 5e-5
+    assert rel_err(dgamma, gg) < 5e-5
+    assert rel_err(dbeta, gb) < 5e-5
+
+
+def test_pools_and_linear_and_bce():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(40, 64, 28, generator=g).to(DEV)
+    assert rel_err(ncl(K().avgpool2(cl(x))), F.avg_pool1d(x, 2, 2)) < 1e-6
+    dy = torch.randn(40, 64, 14, generator=g).to(DEV)
+    xr = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(F.avg_pool1d(xr, 2, 2), xr, dy)
+    assert rel_err(ncl(K().avgpool2(cl(dy), backward=True)), gx) < 1e-6
+    x7 = torch.randn(40, 128, 7, generator=g).to(DEV)
+    feat = K().avgpool_full(cl(x7))
+    assert rel_err(feat, F.avg_pool1d(x7, 7, 1).view(40, -1)) < 1e-6
+    dfeat = torch.randn(40, 128, generator=g).to(DEV)
+    assert rel_err(ncl(K().avgpool_full_bwd(dfeat, 7, torch.float32)), (dfeat / 7).unsqueeze(-1).expand(40, 128, 7)) < 1e-6
+    # linear head: rows = sequences, K = 20*F
+    f = torch.randn(6, 20 * 128, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(2, 20 * 128, generator=g) * 0.02).to(DEV).requires_grad_(True)
+    b = torch.randn(2, generator=g).to(DEV).requires_grad_(True)
+    t = torch.tensor([[1., 0.]] * 3 + [[0., 1.]] * 3, device=DEV)
+    out_ref = F.linear(f, w, b)
+    loss_ref = F.binary_cross_entropy_with_logits(out_ref, t)
+    gf, gw, gb = torch.autograd.grad(loss_ref, [f, w, b])
+    out = K().linear_fwd(f.detach(), w.detach(), b.detach())
+    assert rel_err(out, out_ref) < 1e-5
+    loss, dl = K().bce_with_logits(out, t)
+    assert abs(float(loss) - float(loss_ref)) < 1e-6
+    dfeat, dw, db = K().linear_bwd(dl, f.detach(), w.detach())
+    assert rel_err(dfeat, gf) < 1e-5 and rel_err(dw, gw) < 1e-5 and rel_err(db, gb) < 1e-5
+
+
+def test_dropout_mask_is_reproducible_and_unbiased():
+    x = torch.ones(64, 28, 32, device=DEV)
+    a = K().dropout_(x.clone(), 0.2, 1234)
+    b = K().dropout_(x.clone(), 0.2, 1234)
+    c = K().dropout_(x.clone(), 0.2, 99)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    kept = (a > 0).float().mean().item()
+    assert abs(kept - 0.8) < 0.01
+    assert abs(float(a.max()) - 1.25) < 1e-6
+    off = torch.tensor([5], dtype=torch.int64, device=DEV)
+    d = K().dropout_(x.clone(), 0.2, 1234, off)
+    assert not torch.equal(a, d)
+
+
+def test_fused_optimizers_match_torch():
+    from deepards_b200 import _lib
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(12)
+    p0 = torch.randn(10007, generator=g).to(DEV)
+    grads = [(torch.randn(10007, generator=g) * 0.05).to(DEV) for _ in range(3)]
+    # SGD nesterov with the reference's clamp hook
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([p_ref], lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    p = p0.clone()
+    m = torch.zeros_like(p)
+    for i, gr in enumerate(grads):
+        p_ref.grad = gr.clamp(-0.01, 0.01)
+        opt.step()
+        _lib.call("dards_clamp_sgd_nesterov", p.data_ptr(), gr.data_ptr(), m.data_ptr(), p.numel(), 1e-3, 0.9, 1e-4, 0.01,
+                  1.0, 1 if i == 0 else 0, st)
+    assert rel_err(p, p_ref.detach()) < 1e-6
+    # Adam
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p = p0.clone()
+    ea, es = torch.zeros_like(p), torch.zeros_like(p)
+    for i, gr in enumerate(grads):
+        p_ref.grad = gr.clone()
+        opt.step()
+        _lib.call("dards_clamp_adam", p.data_ptr(), gr.data_ptr(), ea.data_ptr(), es.data_ptr(), p.numel(), 1e-3, 0.9,
+                  0.999, 1e-8, 0.0, 1.0, i + 1, st)
+    assert rel_err(p, p_ref.detach()) < 1e-5
