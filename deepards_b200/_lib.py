@@ -19,6 +19,7 @@ _SIGNATURES = {
     "dards_version": [],
     "dards_last_error": [],
     "dards_device_supported": [],
+    "dards_launch_count": [],
     "dards_pack_conv_weight": [P, P, P, I, I, I, I, P],
     "dards_conv1d_fwd": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "dards_conv1d_dgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
@@ -42,7 +43,7 @@ _SIGNATURES = {
     "dards_clamp_adam": [P, P, P, P, LL, F, F, F, F, F, F, I, P],
     "dards_tc_debug_set": [I, I],
 }
-_RESTYPES = {"dards_last_error": ctypes.c_char_p, "dards_conv1d_wgrad_workspace_bytes": c_longlong}
+_RESTYPES = {"dards_last_error": ctypes.c_char_p, "dards_launch_count": c_longlong, "dards_conv1d_wgrad_workspace_bytes": c_longlong}
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 

@@ -66,6 +66,12 @@ def run_plan(net, backbone, linear, x, group, mode, dropout_key=()):
     """Common entry of every module forward: pick/build the plan, run it through autograd."""
     n = x.numel() // engine.SEQ_LEN
     training = backbone.training
+    if not training and backbone.network_name.startswith("resnet"):
+        # eval() on the reference ResNet would normalise with the running statistics; the reference never does
+        # that on this path (model.eval() is commented out, train_ards_detector.py:448), and a silent switch to
+        # batch statistics here would be a different function.
+        raise NotImplementedError("deepards_b200 ResNet implements training-mode BatchNorm (batch statistics) only; "
+                                  "keep the module in train() mode as train_ards_detector.py does")
     plan = engine.get_plan(net, backbone, linear, n, group, module_precision(net), mode,
                            dropout=dropout_key if training else (), update_running=training)
     params = [p for _, p in plan.params]

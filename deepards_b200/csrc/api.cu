@@ -8,6 +8,9 @@ namespace dards {
 
 static thread_local char g_err[512] = "";
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -70,6 +73,8 @@ extern "C" {
 int dards_version(void) { return 1; }
 
 const char* dards_last_error(void) { return g_err; }
+
+long long dards_launch_count(void) { return g_launches; }
 
 int dards_device_supported(void) {
   int dev = 0;

@@ -9,6 +9,7 @@
 namespace dards {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of the library goes through DARDS_CHECK_LAUNCH
 
 #define DARDS_CHECK_ARG(cond, ...)            \
   do {                                        \
@@ -25,6 +26,7 @@ void set_error(const char* fmt, ...);
       ::dards::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));  \
       return DARDS_ERR_CUDA;                                                       \
     }                                                                              \
+    ::dards::count_launch();                                                       \
   } while (0)
 
 // ---- element type traits: activations are fp32 or bf16, arithmetic is always fp32 ----

@@ -155,8 +155,8 @@ class DataParallelTrainer(object):
     def _backward_overlapped(self, plan):
         """Replay the backward in segments; after each segment the comm stream reduces the buckets that became
         complete.  Buckets are suffixes of the flat buffer (backward finishes the last layers first)."""
-        if plan.bwd_serial + 1 != plan.fwd_serial:
-            raise RuntimeError("backward() without a matching forward()")
+        if plan.bwd_serial == plan.fwd_serial:
+            raise RuntimeError("backward() without a new forward()")
         cur = torch.cuda.current_stream(self.device)
         st = cur.cuda_stream
         marks = dict((idx, off) for off, idx in plan.bwd_marks)  # call index -> offset complete from there on

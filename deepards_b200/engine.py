@@ -529,9 +529,9 @@ class Plan(object):
         self.fwd_serial += 1
 
     def run_backward(self):
-        if self.bwd_serial + 1 != self.fwd_serial:
-            raise RuntimeError("backward() without a matching forward(): the plan's saved activations belong to "
-                               "forward #%d, backward #%d was requested" % (self.fwd_serial, self.bwd_serial + 1))
+        if self.bwd_serial == self.fwd_serial:
+            raise RuntimeError("backward() without a new forward(): forward #%d has already been back-propagated "
+                               "(in-place backward kernels consumed its buffers)" % self.fwd_serial)
         self.bwd.run(self._stream())
         self.bwd_serial = self.fwd_serial
 

@@ -46,6 +46,8 @@ typedef enum dards_dtype { DARDS_F32 = 0, DARDS_BF16 = 1 } dards_dtype;
 /* ---- library ---------------------------------------------------------------------- */
 int dards_version(void);                 /* ABI version, bumped on any signature change */
 const char* dards_last_error(void);      /* thread-local, never NULL */
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+long long dards_launch_count(void);
 /* 1 if the device behind the current context is compute capability 10.x (B200). */
 int dards_device_supported(void);
 

@@ -73,3 +73,52 @@ def check_grads_against_golden(z, grads, tol, what=""):
         n += 1
     assert n > 0
     return worst
+
+
+def golden_grad_errors(z, grads):
+    """{param name: max|mine-golden| / max|golden|} over the full / sampled golden gradients."""
+    out = {}
+    for key in z.files:
+        if key.startswith("grad/"):
+            name = key[5:]
+            out[name] = rel_err(grads[name].detach().cpu(), z[key])
+        elif key.startswith("gradsample/"):
+            name = key[11:]
+            out[name] = rel_err(grads[name].detach().cpu().reshape(-1)[::SAMPLE_STRIDE], z[key])
+        elif key.startswith("nograd/"):
+            name = key[7:]
+            g = grads.get(name)
+            assert g is None or float(torch.as_tensor(g).abs().max()) == 0.0, name
+    return out
+
+
+def conditioned_grad_check(mine, ref32, ref64, tol, what=""):
+    """The fp32 gate of the parity tests.
+
+    A gradient tensor passes if it is within `tol` (max-abs relative) of the fp32 reference result, OR -- where
+    the reference arithmetic itself is ill-conditioned -- if it is as close to the exact (fp64) gradient as the
+    fp32 reference is (factor 3).  Why the second clause exists: with ~10^6 ReLU / max-pool decisions per step a
+    handful of pre-activations sit within fp32 rounding of zero, and a flipped decision moves a whole gradient
+    tensor by 1e-3..5e-2 of its max.  The reference's own fp32-vs-fp64 difference shows exactly that (DESIGN.md,
+    "Parity"), so no independent fp32 implementation can be held to 1e-4 on those tensors.
+    Returns (worst strict error, number of tensors that needed the conditioned clause)."""
+    worst, conditioned, bad = 0.0, 0, []
+    for k, g64 in ref64.items():
+        m = mine[k].detach().cpu()
+        d = rel_err(m, ref32[k])
+        if d <= tol:
+            worst = max(worst, d)
+            continue
+        e_ref = rel_err(ref32[k], g64)
+        e_mine = rel_err(m, g64)
+        if e_mine <= max(tol, 3.0 * e_ref):
+            conditioned += 1
+        else:
+            bad.append("%s: |b200-ref32| %.2e, |b200-fp64| %.2e, |ref32-fp64| %.2e" % (k, d, e_mine, e_ref))
+    assert not bad, "%s gradients out of tolerance:\n  %s" % (what, "\n  ".join(bad))
+    return worst, conditioned
+
+
+def oracle_fp64(sd, x, t, **kw):
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    return O.forward_backward(sd64, x.double(), t.double(), **kw)

@@ -1,0 +1,172 @@
+"""CPU: the drop-in boundary -- C-ABI symbols, module interface, registries, host-side data-parallel logic.
+No kernel is launched here (there is no GPU in the build container)."""
+import io
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import cnn_linear_oracle as O  # noqa: E402
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from deepards_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "deepards_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(dards_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes binding and header disagree"
+    assert lib.dards_version() == 1
+    # the shared object is self-contained: it must not need libcuda / libcudart at load time
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libcudart" not in out
+
+
+def test_argument_validation_returns_error_codes_not_crashes():
+    from deepards_b200 import _lib
+    lib = _lib.load()
+    rc = lib.dards_conv1d_fwd(None, None, None, None, 1, 56, 56, 64, 64, 64, 64, 0, 3, 1, 1, 0, 0, None)
+    assert rc == -1 and "null pointer" in _lib.last_error()
+    rc = lib.dards_conv1d_fwd(16, 16, 16, None, 1, 56, 55, 64, 64, 64, 64, 0, 3, 1, 1, 0, 0, None)
+    assert rc == -1 and "l_out" in _lib.last_error()
+    rc = lib.dards_linear_fwd(16, 16, 16, 16, 1, 128, 99, None)
+    assert rc == -1
+    with pytest.raises(RuntimeError, match="deepards_b200"):
+        _lib.call("dards_stem_fwd", 16, 16, 16, 16, 16, 16, 16, 1, 20, 48, 48, 1e-5, 0, 0, None)  # C0 = 48 unsupported
+
+
+@pytest.mark.parametrize("backbone", ["resnet18", "densenet18"])
+def test_state_dict_keys_shapes_and_module_protocol(backbone):
+    import deepards_b200 as D
+    bb = getattr(D, backbone)()
+    net = D.CNNLinearNetwork(bb, 20, 0)
+    ref = O.cnn_linear_state(backbone, seed=0)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref.keys())  # same names, same order as the reference's modules
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    net.load_state_dict(ref, strict=True)
+    assert net.seq_size == 224 and net.breath_block is bb
+    assert bb.network_name == backbone
+    assert bb.n_out_filters == (512 if backbone == "resnet18" else 128)
+    assert net.linear_final.in_features == 20 * bb.n_out_filters
+    assert all(isinstance(p, torch.nn.Parameter) for p in net.parameters())
+    if backbone == "densenet18":
+        ks, st, pd = bb.conv_info()
+        assert len(ks) == len(st) == len(pd) == 2 + 8 * 2 + 3 * 2
+        assert bb.drop_rate == 0.2 and isinstance(bb.avgpool, torch.nn.AvgPool1d)
+        assert hasattr(bb, "features") and hasattr(bb, "forward_no_pool")
+        assert not any(k.endswith("running_mean") for k in sd)
+    else:
+        assert "breath_block.conv1_alt.weight" in sd and "breath_block.bn2.running_var" in sd
+    # picklable as a whole module (train_ards_detector.py:364)
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    net2 = torch.load(buf, weights_only=False)
+    assert list(net2.state_dict().keys()) == list(sd.keys())
+
+
+def test_init_distribution_matches_reference_recipe():
+    import deepards_b200 as D
+    torch.manual_seed(0)
+    bb = D.resnet18()
+    w = bb.layer3[0].conv1.weight
+    assert abs(float(w.std()) - (2.0 / (3 * 256)) ** 0.5) < 2e-3  # He-normal, fan = k * Cout (resnet.py:115-118)
+    assert float(bb.bn1.weight.min()) == 1.0 and float(bb.bn1.bias.abs().max()) == 0.0
+
+
+def test_cpu_use_fails_loudly_no_fallback():
+    import deepards_b200 as D
+    net = D.CNNLinearNetwork(D.resnet18(initial_planes=16), 20, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(2, 20, 1, 224), None)
+    with pytest.raises(Exception, match="sequence length of 224"):
+        net(torch.zeros(2, 20, 1, 100), None)
+    with pytest.raises(NotImplementedError):
+        D.densenet18(with_fft=True)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "deepards_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle", src, re.M), "%s imports the oracle" % f
+                assert "oracle." not in src and "oracle/" not in src, "%s refers to the oracle" % f
+                # the reference tree may be cited in comments, never touched at run time
+                assert not re.search(r"(sys\.path|open\(|import_module|CDLL)[^\n]*/root/reference", src), f
+
+
+def test_registries_and_install():
+    import types
+    import deepards_b200 as D
+    assert set(["resnet18", "densenet18"]) <= set(D.base_networks)
+    assert D.network_heads["cnn_linear"] is D.CNNLinearNetwork
+    fake = types.ModuleType("train_ards_detector")
+    fake.base_networks = {"resnet18": object(), "vgg11": "kept"}
+    D.install(fake)
+    assert fake.base_networks["resnet18"] is D.resnet18 and fake.base_networks["vgg11"] == "kept"
+    assert fake.CNNLinearNetwork is D.CNNLinearNetwork
+
+
+def test_shard_bounds_live_ranges_and_buckets():
+    from deepards_b200 import data_parallel as dp
+    import deepards_b200 as D
+    for batch, world in [(256, 8), (10, 4), (3, 8), (16, 1)]:
+        spans = [dp.shard_bounds(batch, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == batch
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+    net = D.CNNLinearNetwork(D.resnet18(initial_planes=16), 20, 0)
+    layout, total = dp.param_layout(net)
+    assert all(off % 4 == 0 for _, _, off in layout) and total % 4 == 0
+    dead = set(id(p) for n, p in net.named_parameters() if any(s in n for s in (".conv1_alt.", "block.conv2.", "block.bn2.")))
+    live = set(id(p) for _, p in net.named_parameters()) - dead
+    ranges = dp.live_ranges(layout, live)
+    covered = sum(e - b for b, e in ranges)
+    assert covered == sum((p.numel() + 3) // 4 * 4 for _, p in net.named_parameters() if id(p) in live)
+    assert len(ranges) == 3  # conv1 | bn1 | everything after the unused stem parameters
+    buckets = dp.make_buckets(1000, [900, 700, 650, 100], 200)
+    assert buckets == [(700, 1000), (100, 700), (0, 100)]
+    assert dp.make_buckets(50, [], 10) == [(0, 50)]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from deepards_b200 import data_parallel as dp
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    red = dp.BucketedAllReduce()
+    for b, e in dp.make_buckets(1000, [800, 300], 100):
+        red.reduce(flat, b, e)
+    red.wait()
+    q.put((rank, float(flat.sum()), float(flat[999])))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect_sum = float(torch.arange(1000, dtype=torch.float32).sum()) * 3
+    for rank, s, last in res:
+        assert abs(s - expect_sum) < 1e-3 and last == 999 * 3
