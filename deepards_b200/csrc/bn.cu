@@ -196,31 +196,61 @@ __global__ void __launch_bounds__(BN_THREADS)
   }
 }
 
-__global__ void reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out, int rows, int c,
-                                   int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
+// 256 threads = 32 channels x 8 row lanes; fixed summation order -> deterministic
+constexpr int RR_LANES = 8;
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                          int rows, int c, int accumulate) {
+  __shared__ float red[RR_LANES][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += part[(size_t)r * c + i];
-  out[i] = accumulate ? out[i] + s : s;
+  if (i < c)
+    for (int r = rl; r < rows; r += RR_LANES) s += part[(size_t)r * c + i];
+  red[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && i < c) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < RR_LANES; ++k) t += red[k][cl];
+    out[i] = accumulate ? out[i] + t : t;
+  }
 }
 
-__global__ void bn_running_update_kernel(const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
-                                         float* __restrict__ rm, float* __restrict__ rv, long long* nbt, int n_groups,
-                                         int rows, int c, float momentum, float eps) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && nbt) *nbt += n_groups;
-  if (i >= c) return;
-  float m = rm[i], v = rv[i];
+// nn.BatchNorm1d updates its running statistics once per group, in order:  r <- (1-m) r + m v_g,  g = 0..G-1.
+// Closed form (SURVEY.md hard part 6):  r_G = (1-m)^G r_0 + m * sum_g (1-m)^(G-1-g) v_g  -- a weighted reduction,
+// done here by 8 row lanes per channel instead of a G-long dependent chain.
+__global__ void __launch_bounds__(256)
+    bn_running_update_kernel(const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                             float* __restrict__ rm, float* __restrict__ rv, long long* nbt, int n_groups, int rows, int c,
+                             float momentum, float eps) {
+  __shared__ float red_m[RR_LANES][33], red_v[RR_LANES][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += n_groups;
   const float unbias = rows > 1 ? (float)rows / (float)(rows - 1) : 1.f;
-  for (int g = 0; g < n_groups; ++g) {
-    float r = save_rstd[(size_t)g * c + i];
-    float var = fmaxf(1.f / (r * r) - eps, 0.f) * unbias;
-    m = (1.f - momentum) * m + momentum * save_mean[(size_t)g * c + i];
-    v = (1.f - momentum) * v + momentum * var;
+  const float lg = log2f(1.f - momentum);
+  float sm = 0.f, sv = 0.f;
+  if (i < c)
+    for (int g = rl; g < n_groups; g += RR_LANES) {
+      const float w = momentum * exp2f(lg * (float)(n_groups - 1 - g));
+      const float r = save_rstd[(size_t)g * c + i];
+      sm = fmaf(w, save_mean[(size_t)g * c + i], sm);
+      sv = fmaf(w, fmaxf(1.f / (r * r) - eps, 0.f) * unbias, sv);
+    }
+  red_m[rl][cl] = sm;
+  red_v[rl][cl] = sv;
+  __syncthreads();
+  if (rl == 0 && i < c) {
+    float tm = 0.f, tv = 0.f;
+#pragma unroll
+    for (int k = 0; k < RR_LANES; ++k) {
+      tm += red_m[k][cl];
+      tv += red_v[k][cl];
+    }
+    const float decay = exp2f(lg * (float)n_groups);
+    rm[i] = decay * rm[i] + tm;
+    rv[i] = decay * rv[i] + tv;
   }
-  rm[i] = m;
-  rv[i] = v;
 }
 
 // ---- host launchers ------------------------------------------------------------------------------
@@ -265,14 +295,14 @@ int launch_gbn_bwd(const void* dout, const void* x, const void* mask_src, const 
 
 int launch_reduce_rows(const float* part, float* out, int rows, int c, int accumulate, cudaStream_t st) {
   if (c == 0) return DARDS_OK;
-  reduce_rows_kernel<<<ceil_div(c, 128), 128, 0, st>>>(part, out, rows, c, accumulate);
+  reduce_rows_kernel<<<ceil_div(c, 32), 256, 0, st>>>(part, out, rows, c, accumulate);
   DARDS_CHECK_LAUNCH("reduce_rows");
   return DARDS_OK;
 }
 
 int launch_bn_running_update(const float* save_mean, const float* save_rstd, float* rm, float* rv, long long* nbt,
                              int n_groups, int rows, int c, float momentum, float eps, cudaStream_t st) {
-  bn_running_update_kernel<<<ceil_div(c, 128), 128, 0, st>>>(save_mean, save_rstd, rm, rv, nbt, n_groups, rows, c,
+  bn_running_update_kernel<<<ceil_div(c, 32), 256, 0, st>>>(save_mean, save_rstd, rm, rv, nbt, n_groups, rows, c,
                                                              momentum, eps);
   DARDS_CHECK_LAUNCH("bn_running_update");
   return DARDS_OK;

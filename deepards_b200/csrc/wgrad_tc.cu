@@ -1,0 +1,325 @@
+// tcgen05 weight-gradient kernel for Conv1d (bf16 operands, fp32 accumulation in TMEM, fp32 output).
+//
+//   dW[t][co][ci] = sum over rows k=(breath n, position q) of dout[k, co] * in[k shifted by tap t, ci]
+//
+// GEMM view: D_t[co, ci] = A^T B_t with the REDUCTION over positions.  Channels-last activations make both
+// operands "MN-major" in shared memory: a TMA box of (64 channels x R rows) lands as R rows of 128 bytes, row =
+// reduction index, which is exactly the canonical SWIZZLE_128B MN-major UMMA layout (8-row groups 1024 B apart =
+// SBO, 64-channel chunks LBO apart).  No transposition anywhere.
+//
+// One TMA load per operand serves all taps: each breath is staged with a zero halo row on both sides
+// ([0, dout[0..L-1], 0] and the input shifted by two rows), the halo coming for free from the TMA
+// out-of-bounds fill.  Tap t then multiplies the SAME staged input tile, read through a descriptor whose start
+// address is advanced by t rows (t * 128 B); where the shifted rows run into the neighbouring breath they meet a
+// zero halo row of dout, so nothing leaks across breaths.  Stride-2 convolutions stage the two parity planes of
+// the input (4-D view (C, 2, L/2, N)) as two tiles.
+//
+// Tile: 128 output channels (TMEM lanes) x up to 128 input channels (columns) x up to 3 taps (3 accumulators =
+// 384 TMEM columns).  Split-K over groups of breaths; every CTA writes its fp32 partial tile and a second kernel
+// reduces the partials in a fixed order (deterministic) into the parameter's (Cout, Cin, K) layout.
+#include "tc_common.cuh"
+
+namespace dards {
+
+constexpr int WG_TC_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int WG_RMAX = 128;             // reduction rows per stage (multiple of 16)
+constexpr int WG_CHUNK_A = WG_RMAX * 128;          // bytes of one 64-channel chunk of the dout tile
+constexpr int WG_CHUNK_B = (WG_RMAX + 8) * 128;    // input tile: + 8 zero rows for the shifted taps
+constexpr int WG_A_BYTES = 2 * WG_CHUNK_A;         // 128 output channels
+constexpr int WG_B_BYTES = 2 * WG_CHUNK_B;         // 128 input channels
+constexpr int WG_MAX_TAPS = 3;
+constexpr int WG_SMEM_LIMIT = 227 * 1024;
+
+struct WgTcParams {
+  int n_btiles;                // 1 (stride 1) or 2 (stride 2: one per parity plane)
+  int b_plane[2], b_start[2];  // plane / first-row coordinates of the staged input tiles
+  int a_start;                 // first-row coordinate of the staged dout tile (-1 with halo, 0 without)
+  int n_taps;
+  int tap_btile[WG_MAX_TAPS], tap_shift[WG_MAX_TAPS];
+  int p_rows;                  // rows staged per breath (L + 2*halo)
+  int nb;                      // breaths per stage
+  int r_pad;                   // nb*p_rows rounded up to 16
+  int n_units;                 // ceil(n_breaths / nb): reduction units
+  int units_per_split;
+  int c_in, c_out;
+  int n_ci_tiles, n_co_tiles;
+  int stages, stage_bytes;
+  int base_offset_mode;        // 0: descriptor base_offset = (start >> 7) & 7, 1: always 0
+};
+
+__global__ void __launch_bounds__(WG_TC_THREADS, 1)
+    tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    float* __restrict__ partial, const WgTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + p.stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t done_bar = bar_base + 8u * 8;
+  const uint32_t tmem_slot = bar_base + 8u * 9;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int co0 = (tile / p.n_ci_tiles) * 128, ci0 = (tile % p.n_ci_tiles) * 128;
+  const int ci_n = (p.c_in - ci0) >= 128 ? 128 : ((p.c_in - ci0 + 63) / 64) * 64;  // MMA N: 64 or 128
+  const int co_chunks = (p.c_out - co0) > 64 ? 2 : 1, ci_chunks = ci_n / 64;
+  const int u_begin = split * p.units_per_split;
+  int u_end = u_begin + p.units_per_split;
+  if (u_end > p.n_units) u_end = p.n_units;
+  const int n_iters = u_end > u_begin ? u_end - u_begin : 0;
+
+  // Rows that TMA never writes must be ZERO (dout: they multiply shifted input rows) or at least finite
+  // (input): clear the whole operand area once.  generic-proxy writes -> fence -> visible to the async proxy.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem_gen);
+    const int n16 = (p.stages * p.stage_bytes) / 16;
+    for (int i = threadIdx.x; i < n16; i += WG_TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int rows = p.nb * p.p_rows;  // rows written by TMA per chunk
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)rows * 128u * (uint32_t)(co_chunks + p.n_btiles * ci_chunks);
+      for (int it = 0; it < n_iters; ++it) {
+        const int n0 = (u_begin + it) * p.nb;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * p.stage_bytes;
+        mbar_arrive_expect_tx(full_bar(stage), tx);
+        for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * WG_CHUNK_A, &tm_a, full_bar(stage), co0 + c * 64, 0, p.a_start, n0);
+        for (int b = 0; b < p.n_btiles; ++b) {
+          const uint32_t sb = sa + WG_A_BYTES + b * WG_B_BYTES;
+          for (int c = 0; c < ci_chunks; ++c)
+            tma_load_4d(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0);
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = ci_n, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(ci_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      const int k_steps = p.r_pad / 16;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * p.stage_bytes;
+        for (int kk = 0; kk < k_steps; ++kk) {
+          const uint64_t a_desc = make_sw128_desc(sa + kk * 2048, WG_CHUNK_A >> 4, 1024 >> 4, 1, 0);
+          for (int t = 0; t < p.n_taps; ++t) {
+            const uint32_t sb = sa + WG_A_BYTES + p.tap_btile[t] * WG_B_BYTES + kk * 2048 + p.tap_shift[t] * 128;
+            const uint32_t bo = p.base_offset_mode == 0 ? ((sb >> 7) & 7u) : 0u;
+            const uint64_t b_desc = make_sw128_desc(sb, WG_CHUNK_B >> 4, 1024 >> 4, 1, bo);
+            umma_bf16(tmem_base + (uint32_t)t * 128u, a_desc, b_desc, idesc, (it | kk) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // epilogue: partial[split][t][co][ci] (fp32); thread = output channel, 16 input channels per TMEM load
+    const int quarter = warp & 3;
+    const int co = co0 + quarter * 32 + lane;
+    if (n_iters > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int t = 0; t < p.n_taps; ++t) {
+      float* dst = partial + (((size_t)split * p.n_taps + t) * p.c_out + co) * p.c_in + ci0;
+      for (int c0 = 0; c0 < ci_n; c0 += 16) {
+        uint32_t v[16];
+        if (n_iters > 0) {
+          tmem_ld16(t_row + (uint32_t)t * 128u + (uint32_t)c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (co < p.c_out && ci0 + c0 < p.c_in) {  // c_in is a multiple of 16
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dw[co][ci][t] (+)= sum_s partial[s][t][co][ci]
+__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int ktaps,
+                                       int c_in, int c_out, int accumulate) {
+  const int per = ktaps * c_in * c_out;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+    // i indexes [t][co][ci] so that the reads are coalesced
+    const int ci = i % c_in, co = (i / c_in) % c_out, t = i / (c_in * c_out);
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * per + i];
+    const size_t o = ((size_t)co * c_in + ci) * ktaps + t;
+    dw[o] = accumulate ? dw[o] + s : s;
+  }
+}
+
+struct WgPlan {
+  WgTcParams p;
+  int splits;
+  bool ok;
+};
+
+static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride, int pad) {
+  WgPlan w{};
+  w.ok = false;
+  WgTcParams& p = w.p;
+  if (!((ktaps == 3 && pad == 1) || (ktaps == 1 && pad == 0))) return w;
+  if (stride != 1 && stride != 2) return w;
+  if (c_in % 16 || c_out % 8 || l_in != l_out * stride) return w;
+  const int halo = ktaps == 3 ? 1 : 0;
+  p.p_rows = l_out + 2 * halo;
+  p.a_start = -halo;
+  p.n_taps = ktaps;
+  if (stride == 1) {
+    p.n_btiles = 1;
+    p.b_plane[0] = 0;
+    p.b_start[0] = -2 * halo;  // staged row i = in[i - 2]; tap t of dout row j pairs with staged row j + t
+    for (int t = 0; t < ktaps; ++t) {
+      p.tap_btile[t] = 0;
+      p.tap_shift[t] = t;
+    }
+  } else if (ktaps == 3) {
+    // in[2q + t - 1]: t = 1 -> plane 0 row q; t = 0 -> plane 1 row q-1; t = 2 -> plane 1 row q
+    p.n_btiles = 2;
+    p.b_plane[0] = 0; p.b_start[0] = -1;  // staged row i = plane0[i - 1]: dout row j=q+1 pairs with row j
+    p.b_plane[1] = 1; p.b_start[1] = -2;  // staged row i = plane1[i - 2]: tap 0 -> row j, tap 2 -> row j + 1
+    p.tap_btile[0] = 1; p.tap_shift[0] = 0;
+    p.tap_btile[1] = 0; p.tap_shift[1] = 0;
+    p.tap_btile[2] = 1; p.tap_shift[2] = 1;
+  } else {
+    p.n_btiles = 1;
+    p.b_plane[0] = 0; p.b_start[0] = 0;
+    p.tap_btile[0] = 0; p.tap_shift[0] = 0;
+  }
+  p.nb = WG_RMAX / p.p_rows;
+  if (p.nb < 1) return w;
+  if (p.nb > 256) p.nb = 256;
+  p.r_pad = (p.nb * p.p_rows + 15) / 16 * 16;
+  p.n_units = ceil_div(n_breaths, p.nb);
+  p.c_in = c_in; p.c_out = c_out;
+  p.n_ci_tiles = ceil_div(c_in, 128);
+  p.n_co_tiles = ceil_div(c_out, 128);
+  p.stage_bytes = WG_A_BYTES + p.n_btiles * WG_B_BYTES;
+  p.stages = (WG_SMEM_LIMIT - 2048) / p.stage_bytes;
+  if (p.stages > 4) p.stages = 4;
+  if (p.stages < 2) return w;
+  const int tiles = p.n_ci_tiles * p.n_co_tiles;
+  int splits = (2 * sm_count() + tiles - 1) / tiles;  // ~2 waves: the partial-tile epilogue is short
+  const int max_by_units = (p.n_units + 3) / 4;       // at least 4 reduction units per CTA
+  if (splits > max_by_units) splits = max_by_units;
+  if (splits < 1) splits = 1;
+  p.units_per_split = ceil_div(p.n_units, splits);
+  w.splits = ceil_div(p.n_units, p.units_per_split);
+  p.base_offset_mode = g_dbg_base_offset_mode >= 0 ? g_dbg_base_offset_mode : 0;
+  w.ok = true;
+  return w;
+}
+
+long long tc_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps) {
+  // the split count does not depend on stride/pad beyond validity; use the stride-1 plan shape
+  WgPlan w = wg_plan(n_breaths, l_out, l_out, c_in, c_out, ktaps, 1, ktaps == 3 ? 1 : 0);
+  if (!w.ok) return 0;
+  return (long long)w.splits * ktaps * c_in * c_out * (long long)sizeof(float);
+}
+
+int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, void* workspace, long long workspace_bytes,
+                  int n_breaths, int l_in, int l_out, int c_in, int c_out, int in_stride, int dout_stride, int ktaps,
+                  int stride, int pad, cudaStream_t st) {
+  WgPlan w = wg_plan(n_breaths, l_in, l_out, c_in, c_out, ktaps, stride, pad);
+  if (!w.ok) {
+    set_error("tcgen05 wgrad: unsupported shape (k=%d s=%d p=%d cin=%d cout=%d l=%d)", ktaps, stride, pad, c_in, c_out, l_in);
+    return DARDS_ERR_UNSUPPORTED;
+  }
+  DARDS_CHECK_ARG(in_stride % 8 == 0 && dout_stride % 8 == 0, "tcgen05 wgrad: row strides must be multiples of 8");
+  DARDS_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0,
+                  "tcgen05 wgrad: operands must be 16-byte aligned");
+  const long long need = (long long)w.splits * ktaps * c_in * c_out * (long long)sizeof(float);
+  DARDS_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "tcgen05 wgrad: workspace too small (%lld < %lld)",
+                  workspace_bytes, need);
+  WgTcParams& p = w.p;
+  CUtensorMap tm_a, tm_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)c_out, 1, (cuuint64_t)l_out, (cuuint64_t)n_breaths};
+    cuuint64_t str[3] = {(cuuint64_t)dout_stride * 2, (cuuint64_t)dout_stride * 2, (cuuint64_t)dout_stride * l_out * 2};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)p.p_rows, (cuuint32_t)p.nb};
+    int rc = make_bf16_map(&tm_a, dout, 4, dims, str, box, true);
+    if (rc) return rc;
+  }
+  {
+    const int l_plane = l_in / stride;
+    cuuint64_t dims[4] = {(cuuint64_t)c_in, (cuuint64_t)stride, (cuuint64_t)l_plane, (cuuint64_t)n_breaths};
+    cuuint64_t str[3] = {(cuuint64_t)in_stride * 2, (cuuint64_t)in_stride * stride * 2, (cuuint64_t)in_stride * l_in * 2};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)p.p_rows, (cuuint32_t)p.nb};
+    int rc = make_bf16_map(&tm_b, in, 4, dims, str, box, true);
+    if (rc) return rc;
+  }
+  const int smem = p.stages * p.stage_bytes + 1024 + 256;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("tcgen05 wgrad: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return DARDS_ERR_CUDA;
+    }
+    attr_smem = smem;
+  }
+  dim3 grid(p.n_ci_tiles * p.n_co_tiles, w.splits);
+  tc_wgrad_kernel<<<grid, WG_TC_THREADS, smem, st>>>(tm_a, tm_b, static_cast<float*>(workspace), p);
+  DARDS_CHECK_LAUNCH("tc_wgrad");
+  const int per = ktaps * c_in * c_out;
+  int blocks = ceil_div(per, 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  tc_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(workspace), dw, w.splits, ktaps, c_in, c_out,
+                                                 accumulate);
+  DARDS_CHECK_LAUNCH("tc_wgrad_reduce");
+  return DARDS_OK;
+}
+
+}  // namespace dards

@@ -161,15 +161,14 @@ class Plan(object):
         return c
 
     def _tc_ok(self, c, direction):
-        if self.simt_only:
-            return False
-        if c.cin % 8 or c.cout % 8:
-            return False
-        if direction == "dgrad" and c.stride != 1:
+        """tcgen05 path for this conv?  (bf16 plans only; everything else runs the CUDA-core kernels)"""
+        if self.simt_only or c.stride not in (1, 2):
             return False
         if direction == "wgrad":
-            return False
-        return c.stride in (1, 2)
+            if "wgrad" in _conv_impl_override():
+                return False
+            return ((c.k == 3 and c.pad == 1) or (c.k == 1 and c.pad == 0)) and c.cin % 16 == 0 and c.cout % 8 == 0
+        return c.cin % 8 == 0 and c.cout % 8 == 0
 
     def conv_fwd(self, c, src, src_stride, dst, dst_stride, l_in, dst_ptr_off=0):
         l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
@@ -363,8 +362,9 @@ class Plan(object):
                              d_out.data_ptr(), cout, rows, cout, 0)
                 self.conv_wgrad(r["cd"], r["a_in"].data_ptr(), cin, d_out.data_ptr(), cout, l_in)
                 d_in = self.scratch("gA", (N, l_in, cin))
-                self.conv_dgrad(r["cd"], d_out.data_ptr(), cout, d_in.data_ptr(), cin, l_in)
-                self.conv_dgrad(r["c1"], da1.data_ptr(), cout, d_in.data_ptr(), cin, l_in, addend=d_in.data_ptr(),
+                # main branch first (writes every position), then the 1x1 stride-2 branch accumulates in place
+                self.conv_dgrad(r["c1"], da1.data_ptr(), cout, d_in.data_ptr(), cin, l_in)
+                self.conv_dgrad(r["cd"], d_out.data_ptr(), cout, d_in.data_ptr(), cin, l_in, addend=d_in.data_ptr(),
                                 addend_stride=cin)
             else:
                 d_in = d_out  # g is the identity-branch gradient: accumulate conv1's dgrad onto it in place

@@ -50,6 +50,10 @@ def conv1d_dgrad(dout, w, l_in, stride, pad, impl=0, out=None, addend=None):
     n, lo, cout = dout.shape
     _, cin, k = w.shape
     kio, koi = pack_conv_weight(w, dout.dtype)
+    if impl == 1 and addend is not None:
+        # the tcgen05 path accumulates in place (TMA reduce-add): out must BE the addend
+        out = addend.clone() if out is None else out.copy_(addend)
+        addend = out
     if out is None:
         out = torch.empty((n, l_in, cin), dtype=dout.dtype, device=dout.device)
     _lib.call("dards_conv1d_dgrad", dout.data_ptr(), (kio if impl == 1 else koi).data_ptr(), out.data_ptr(),
