@@ -127,6 +127,7 @@ def workload_config(args, cpu_sample=None):
                      "%d x %d x 1 x 224 synthetic breaths per GPU (BASELINE.json configs[1])" % (args.backbone, SEQ_PER_GPU, SUB_BATCH),
          "backbone": args.backbone, "sequences_per_gpu": SEQ_PER_GPU, "sub_batch": SUB_BATCH, "precision": "bf16 storage / "
          "tcgen05 convolutions, fp32 statistics, gradients and weights", "parallelism": "dp%d" % args.gpus,
+         "cuda_graph": bool(args.gpus == 1 and not args.no_graph),
          "l2": "working set per step (>1 GB of activations) exceeds the 126 MB L2; 4 resident input batches are rotated"}
     if cpu_sample:
         c["cpu_sample_sequences"] = cpu_sample
@@ -158,7 +159,8 @@ def run_b200(args):
     net = D.CNNLinearNetwork(bb, SUB_BATCH, 0).to(dev)
     net.precision = args.precision
     net.train()
-    trainer = DataParallelTrainer(net, lr=1e-3, optimizer="sgd", weight_decay=1e-4, clip_val=0.01)
+    trainer = DataParallelTrainer(net, lr=1e-3, optimizer="sgd", weight_decay=1e-4, clip_val=0.01,
+                                  use_graph=not args.no_graph)
 
     n_in = 4
     xs_host = [O.synthetic_breaths(SEQ_PER_GPU, seed=1234 + rank * 17 + i).pin_memory() for i in range(n_in)]
@@ -205,9 +207,9 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = lib.dards_launch_count()
+    l0, g0 = lib.dards_launch_count(), trainer.graph_launches
     ms = timed(resident_step, args.steps)
-    launches = lib.dards_launch_count() - l0
+    launches = (lib.dards_launch_count() - l0) + (trainer.graph_launches - g0)
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
@@ -314,6 +316,7 @@ def main():
     ap.add_argument("--backbone", default="resnet18", choices=["resnet18", "densenet18"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,27 +1,63 @@
 // Grouped BatchNorm1d (+residual, +ReLU) forward/backward on channels-last activations.
 //
-// Bandwidth-bound kernels: one CTA owns (one group of `rows` = group*L rows) x (32 channels).  The group
-// tile (<= 2240 x 32 elements) is streamed once from HBM and re-read from L1/L2 for the second and third
-// sweep, so HBM traffic is one read of every input and one write of every output.  Statistics use the
-// two-sweep (mean, then centred sum of squares) formulation for fp32-faithful variance.
+// Bandwidth-bound kernels: one CTA owns (one group of `rows` = group*L rows) x (8 x VEC channels), VEC = the
+// number of elements in a 16-byte access (4 fp32 / 8 bf16).  The group tile (<= 1120 x 128 bytes for a 20-breath
+// sequence) is streamed once from HBM and re-read from L1/L2 for the second and third sweep.  Statistics use
+// the two-sweep (mean, then centred sum of squares) formulation for fp32-faithful variance.
 //
-// thread layout: 256 threads = 32 row lanes x 8 channel quads (4 consecutive channels, one 16-byte
-// (fp32) / 8-byte (bf16) vector access per row).
+// thread layout: 256 threads = 32 row lanes x 8 channel vectors.
 #include "common.cuh"
 
 namespace dards {
 
-constexpr int BN_CT = 32;        // channels per CTA
-constexpr int BN_THREADS = 256;  // 32 row lanes x 8 quads
+constexpr int BN_THREADS = 256;
 constexpr int BN_LANES = 32;
+constexpr int BN_QUADS = 8;
+constexpr int BN_MAXCT = BN_QUADS * 8;  // 64 channels per CTA for bf16, 32 for fp32
 
-// reduce v[4] over the 32 row lanes; result for channel (quad*4+j) is returned to every thread of that quad
-__device__ __forceinline__ void lane_reduce4(float (&v)[4], float (*red)[BN_CT + 1], float* bcast, int rl, int cq) {
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      float2 f = __bfloat1622float2(b);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// reduce v[V] over the 32 row lanes; the total for channel (cq*V + j) is returned to every thread of vector cq
+template <int V>
+__device__ __forceinline__ void lane_reduce(float (&v)[V], float (*red)[BN_MAXCT + 1], float* bcast, int rl, int cq) {
   __syncthreads();  // protect red/bcast from the previous use
 #pragma unroll
-  for (int j = 0; j < 4; ++j) red[rl][cq * 4 + j] = v[j];
+  for (int j = 0; j < V; ++j) red[rl][cq * V + j] = v[j];
   __syncthreads();
-  if (threadIdx.x < BN_CT) {
+  if (threadIdx.x < BN_QUADS * V) {
     float s = 0.f;
 #pragma unroll 8
     for (int r = 0; r < BN_LANES; ++r) s += red[r][threadIdx.x];
@@ -29,170 +65,175 @@ __device__ __forceinline__ void lane_reduce4(float (&v)[4], float (*red)[BN_CT +
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = bcast[cq * 4 + j];
+  for (int j = 0; j < V; ++j) v[j] = bcast[cq * V + j];
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BN_THREADS) gbn_fwd_kernel(const T* x, T* out, const T* res,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, float* __restrict__ save_mean,
-                                                             float* __restrict__ save_rstd, int rows, int c, int x_stride,
-                                                             int out_stride, int res_stride, float eps, int relu) {
-  __shared__ float red[BN_LANES][BN_CT + 1];
-  __shared__ float bcast[BN_CT];
+__global__ void __launch_bounds__(BN_THREADS)
+    gbn_fwd_kernel(const T* x, T* out, const T* res, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ save_mean, float* __restrict__ save_rstd, int rows, int c, int x_stride,
+                   int out_stride, int res_stride, float eps, int relu) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float red[BN_LANES][BN_MAXCT + 1];
+  __shared__ float bcast[BN_MAXCT];
   const int g = blockIdx.y;
   const int rl = threadIdx.x >> 3, cq = threadIdx.x & 7;
-  const int c0 = blockIdx.x * BN_CT + cq * 4;
+  const int c0 = blockIdx.x * (BN_QUADS * V) + cq * V;
   const bool active = c0 < c;
   const size_t row_base = (size_t)g * rows;
   const float inv_n = 1.f / (float)rows;
 
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  float s[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) s[j] = 0.f;
   if (active)
     for (int r = rl; r < rows; r += BN_LANES) {
-      float4 v = Elem<T>::ld4(x + (row_base + r) * x_stride + c0);
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-    }
-  lane_reduce4(s, red, bcast, rl, cq);
-  float mean[4];
+      float v[V];
+      Vec<T>::ld(x + (row_base + r) * x_stride + c0, v);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) mean[j] = s[j] * inv_n;
+      for (int j = 0; j < V; ++j) s[j] += v[j];
+    }
+  lane_reduce<V>(s, red, bcast, rl, cq);
+  float mean[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) mean[j] = s[j] * inv_n;
 
-  float q[4] = {0.f, 0.f, 0.f, 0.f};
+  float q[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) q[j] = 0.f;
   if (active)
     for (int r = rl; r < rows; r += BN_LANES) {
-      float4 v = Elem<T>::ld4(x + (row_base + r) * x_stride + c0);
-      float d0 = v.x - mean[0], d1 = v.y - mean[1], d2 = v.z - mean[2], d3 = v.w - mean[3];
-      q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+      float v[V];
+      Vec<T>::ld(x + (row_base + r) * x_stride + c0, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float d = v[j] - mean[j];
+        q[j] = fmaf(d, d, q[j]);
+      }
     }
-  lane_reduce4(q, red, bcast, rl, cq);
+  lane_reduce<V>(q, red, bcast, rl, cq);
   if (!active) return;
-  float rstd[4], sc[4], sh[4];
+  float sc[V], sh[V];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    rstd[j] = rsqrtf(q[j] * inv_n + eps);
-    // one Newton step: rsqrtf is 2 ulp; the reference divides by sqrt()
-    float v = q[j] * inv_n + eps;
-    rstd[j] = rstd[j] * (1.5f - 0.5f * v * rstd[j] * rstd[j]);
-    sc[j] = rstd[j] * gamma[c0 + j];
+  for (int j = 0; j < V; ++j) {
+    const float var = q[j] * inv_n + eps;
+    float rstd = rsqrtf(var);
+    rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);  // one Newton step: the reference divides by sqrt()
+    sc[j] = rstd * gamma[c0 + j];
     sh[j] = beta[c0 + j] - mean[j] * sc[j];
-  }
-  if (rl == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    if (rl == 0) {
       save_mean[(size_t)g * c + c0 + j] = mean[j];
-      save_rstd[(size_t)g * c + c0 + j] = rstd[j];
+      save_rstd[(size_t)g * c + c0 + j] = rstd;
     }
   }
   for (int r = rl; r < rows; r += BN_LANES) {
-    float4 v = Elem<T>::ld4(x + (row_base + r) * x_stride + c0);
-    v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]);
-    v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
+    float v[V];
+    Vec<T>::ld(x + (row_base + r) * x_stride + c0, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
     if (res) {
-      float4 e = Elem<T>::ld4(res + (row_base + r) * res_stride + c0);
-      v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+      float e[V];
+      Vec<T>::ld(res + (row_base + r) * res_stride + c0, e);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] += e[j];
     }
     if (relu) {
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
     }
-    Elem<T>::st4(out + (row_base + r) * out_stride + c0, v);
+    Vec<T>::st(out + (row_base + r) * out_stride + c0, v);
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
-    gbn_bwd_kernel(const T* dout, const T* x, const T* mask_src,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
-                   const float* __restrict__ save_rstd, T* dx, int accumulate_dx, T* dres, float* __restrict__ dgamma_part,
-                   float* __restrict__ dbeta_part, int rows, int c, int dout_stride, int x_stride, int mask_stride,
-                   int dx_stride, int dres_stride, int relu_mode) {
-  __shared__ float red[BN_LANES][BN_CT + 1];
-  __shared__ float bcast[BN_CT];
+    gbn_bwd_kernel(const T* dout, const T* x, const T* mask_src, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                   T* dx, int accumulate_dx, T* dres, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part,
+                   int rows, int c, int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride,
+                   int relu_mode) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float red[BN_LANES][BN_MAXCT + 1];
+  __shared__ float bcast[BN_MAXCT];
   const int g = blockIdx.y;
   const int rl = threadIdx.x >> 3, cq = threadIdx.x & 7;
-  const int c0 = blockIdx.x * BN_CT + cq * 4;
+  const int c0 = blockIdx.x * (BN_QUADS * V) + cq * V;
   const bool active = c0 < c;
   const size_t row_base = (size_t)g * rows;
   const float inv_n = 1.f / (float)rows;
 
-  float mean[4] = {0, 0, 0, 0}, rstd[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0}, bt[4] = {0, 0, 0, 0};
-  if (active) {
+  float mean[V], rstd[V], sc[V], sh[V];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      mean[j] = save_mean[(size_t)g * c + c0 + j];
-      rstd[j] = save_rstd[(size_t)g * c + c0 + j];
-      gm[j] = gamma[c0 + j];
-      bt[j] = beta[c0 + j];
-    }
+  for (int j = 0; j < V; ++j) {
+    mean[j] = active ? save_mean[(size_t)g * c + c0 + j] : 0.f;
+    rstd[j] = active ? save_rstd[(size_t)g * c + c0 + j] : 0.f;
+    const float gm = active ? gamma[c0 + j] : 0.f, bt = active ? beta[c0 + j] : 0.f;
+    sc[j] = rstd[j] * gm;          // same arithmetic as the forward: y = fmaf(x, sc, sh)
+    sh[j] = bt - mean[j] * sc[j];
   }
   // masked upstream gradient and xhat for one row
-  auto load_row = [&](int r, float (&gv)[4], float (&xh)[4]) {
-    float4 d = Elem<T>::ld4(dout + (row_base + r) * dout_stride + c0);
-    float4 v = Elem<T>::ld4(x + (row_base + r) * x_stride + c0);
-    gv[0] = d.x; gv[1] = d.y; gv[2] = d.z; gv[3] = d.w;
-    xh[0] = (v.x - mean[0]) * rstd[0]; xh[1] = (v.y - mean[1]) * rstd[1];
-    xh[2] = (v.z - mean[2]) * rstd[2]; xh[3] = (v.w - mean[3]) * rstd[3];
-    if (relu_mode == 1) {
-      // same arithmetic as the forward: fmaf(x, sc, sh) with sc = rstd*gamma, sh = beta - mean*sc
-      const float xin[4] = {v.x, v.y, v.z, v.w};
+  auto load_row = [&](int r, float (&gv)[V], float (&xh)[V]) {
+    float v[V];
+    Vec<T>::ld(dout + (row_base + r) * dout_stride + c0, gv);
+    Vec<T>::ld(x + (row_base + r) * x_stride + c0, v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float sc = rstd[j] * gm[j];
-        float y = fmaf(xin[j], sc, bt[j] - mean[j] * sc);
-        if (!(y > 0.f)) gv[j] = 0.f;
-      }
+    for (int j = 0; j < V; ++j) xh[j] = (v[j] - mean[j]) * rstd[j];
+    if (relu_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (!(fmaf(v[j], sc[j], sh[j]) > 0.f)) gv[j] = 0.f;
     } else if (relu_mode == 2) {
-      float4 m = Elem<T>::ld4(mask_src + (row_base + r) * mask_stride + c0);
-      if (!(m.x > 0.f)) gv[0] = 0.f;
-      if (!(m.y > 0.f)) gv[1] = 0.f;
-      if (!(m.z > 0.f)) gv[2] = 0.f;
-      if (!(m.w > 0.f)) gv[3] = 0.f;
+      float m[V];
+      Vec<T>::ld(mask_src + (row_base + r) * mask_stride + c0, m);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (!(m[j] > 0.f)) gv[j] = 0.f;
     }
   };
 
-  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  float s1[V], s2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) s1[j] = s2[j] = 0.f;
   if (active)
     for (int r = rl; r < rows; r += BN_LANES) {
-      float gv[4], xh[4];
+      float gv[V], xh[V];
       load_row(r, gv, xh);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < V; ++j) {
         s1[j] += gv[j];
         s2[j] = fmaf(gv[j], xh[j], s2[j]);
       }
     }
-  lane_reduce4(s1, red, bcast, rl, cq);
-  lane_reduce4(s2, red, bcast, rl, cq);
+  lane_reduce<V>(s1, red, bcast, rl, cq);
+  lane_reduce<V>(s2, red, bcast, rl, cq);
   if (!active) return;
   if (rl == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
       if (dbeta_part) dbeta_part[(size_t)g * c + c0 + j] = s1[j];
       if (dgamma_part) dgamma_part[(size_t)g * c + c0 + j] = s2[j];
     }
   }
-  float k0[4], m1[4], m2[4];
+  float m1[V], m2[V];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    k0[j] = gm[j] * rstd[j];
+  for (int j = 0; j < V; ++j) {
     m1[j] = s1[j] * inv_n;
     m2[j] = s2[j] * inv_n;
   }
   for (int r = rl; r < rows; r += BN_LANES) {
-    float gv[4], xh[4];
+    float gv[V], xh[V], o[V];
     load_row(r, gv, xh);
-    float4 o;
-    o.x = k0[0] * (gv[0] - m1[0] - xh[0] * m2[0]);
-    o.y = k0[1] * (gv[1] - m1[1] - xh[1] * m2[1]);
-    o.z = k0[2] * (gv[2] - m1[2] - xh[2] * m2[2]);
-    o.w = k0[3] * (gv[3] - m1[3] - xh[3] * m2[3]);
-    if (dres) Elem<T>::st4(dres + (row_base + r) * dres_stride + c0, make_float4(gv[0], gv[1], gv[2], gv[3]));
+#pragma unroll
+    for (int j = 0; j < V; ++j) o[j] = sc[j] * (gv[j] - m1[j] - xh[j] * m2[j]);
+    if (dres) Vec<T>::st(dres + (row_base + r) * dres_stride + c0, gv);
     T* dst = dx + (row_base + r) * dx_stride + c0;
     if (accumulate_dx) {
-      float4 e = Elem<T>::ld4(dst);
-      o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+      float e[V];
+      Vec<T>::ld(dst, e);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] += e[j];
     }
-    Elem<T>::st4(dst, o);
+    Vec<T>::st(dst, o);
   }
 }
 
@@ -254,15 +295,18 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- host launchers ------------------------------------------------------------------------------
+static int vec_of(int dtype) { return dtype == DARDS_BF16 ? 8 : 4; }
+
 int launch_gbn_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta, float* save_mean,
                    float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride, int res_stride,
                    float eps, int relu, int dtype, cudaStream_t st) {
-  DARDS_CHECK_ARG(c % 4 == 0 && x_stride % 4 == 0 && out_stride % 4 == 0 && (!res || res_stride % 4 == 0),
-                  "gbn_fwd: channels and strides must be multiples of 4");
+  const int v = vec_of(dtype);
+  DARDS_CHECK_ARG(c % v == 0 && x_stride % v == 0 && out_stride % v == 0 && (!res || res_stride % v == 0),
+                  "gbn_fwd: channels and strides must be multiples of %d", v);
   DARDS_CHECK_ARG(rows > 0, "gbn_fwd: empty group");
   if (n_groups == 0) return DARDS_OK;
   DARDS_CHECK_ARG(n_groups <= 65535, "gbn_fwd: too many groups (%d)", n_groups);
-  dim3 grid(ceil_div(c, BN_CT), n_groups);
+  dim3 grid(ceil_div(c, BN_QUADS * v), n_groups);
   DARDS_DISPATCH_DTYPE(dtype, {
     gbn_fwd_kernel<T><<<grid, BN_THREADS, 0, st>>>(static_cast<const T*>(x), static_cast<T*>(out),
                                                    static_cast<const T*>(res), gamma, beta, save_mean, save_rstd, rows,
@@ -276,13 +320,14 @@ int launch_gbn_bwd(const void* dout, const void* x, const void* mask_src, const 
                    const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
                    float* dgamma_part, float* dbeta_part, int n_groups, int rows, int c, int dout_stride, int x_stride,
                    int mask_stride, int dx_stride, int dres_stride, int relu_mode, int dtype, cudaStream_t st) {
-  DARDS_CHECK_ARG(c % 4 == 0 && dout_stride % 4 == 0 && x_stride % 4 == 0 && dx_stride % 4 == 0,
-                  "gbn_bwd: channels and strides must be multiples of 4");
-  DARDS_CHECK_ARG(relu_mode != 2 || (mask_src && mask_stride % 4 == 0), "gbn_bwd: relu_mode 2 needs mask_src");
-  DARDS_CHECK_ARG(!dres || dres_stride % 4 == 0, "gbn_bwd: dres stride");
+  const int v = vec_of(dtype);
+  DARDS_CHECK_ARG(c % v == 0 && dout_stride % v == 0 && x_stride % v == 0 && dx_stride % v == 0,
+                  "gbn_bwd: channels and strides must be multiples of %d", v);
+  DARDS_CHECK_ARG(relu_mode != 2 || (mask_src && mask_stride % v == 0), "gbn_bwd: relu_mode 2 needs mask_src");
+  DARDS_CHECK_ARG(!dres || dres_stride % v == 0, "gbn_bwd: dres stride");
   if (n_groups == 0) return DARDS_OK;
   DARDS_CHECK_ARG(n_groups <= 65535, "gbn_bwd: too many groups (%d)", n_groups);
-  dim3 grid(ceil_div(c, BN_CT), n_groups);
+  dim3 grid(ceil_div(c, BN_QUADS * v), n_groups);
   DARDS_DISPATCH_DTYPE(dtype, {
     gbn_bwd_kernel<T><<<grid, BN_THREADS, 0, st>>>(
         static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,

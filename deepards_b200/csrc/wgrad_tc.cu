@@ -44,7 +44,7 @@ struct WgTcParams {
   int c_in, c_out;
   int n_ci_tiles, n_co_tiles;
   int stages, stage_bytes;
-  int base_offset_mode;        // 0: descriptor base_offset = (start >> 7) & 7, 1: always 0
+  int base_offset_mode;        // 1 (default): base_offset 0;  0: (start >> 7) & 7 -- kept for the probe only
 };
 
 __global__ void __launch_bounds__(WG_TC_THREADS, 1)
@@ -251,13 +251,17 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return w;
   const int tiles = p.n_ci_tiles * p.n_co_tiles;
-  int splits = (2 * sm_count() + tiles - 1) / tiles;  // ~2 waves: the partial-tile epilogue is short
+  // exactly one wave: tiles * splits <= #SMs (1 CTA per SM: ~200 KB of shared memory each), so no tail wave
+  int splits = tiles >= sm_count() ? 1 : sm_count() / tiles;
   const int max_by_units = (p.n_units + 3) / 4;       // at least 4 reduction units per CTA
   if (splits > max_by_units) splits = max_by_units;
   if (splits < 1) splits = 1;
   p.units_per_split = ceil_div(p.n_units, splits);
   w.splits = ceil_div(p.n_units, p.units_per_split);
-  p.base_offset_mode = g_dbg_base_offset_mode >= 0 ? g_dbg_base_offset_mode : 0;
+  // Measured on B200 (tools/tc_probe.py, profiles/r01_tc_probe.txt): the 128B swizzle is applied to ABSOLUTE shared
+  // memory address bits, so a descriptor whose start is advanced by whole 128-byte rows needs base_offset = 0;
+  // base_offset = (start >> 7) & 7 gives wrong results for the shifted taps.
+  p.base_offset_mode = g_dbg_base_offset_mode >= 0 ? g_dbg_base_offset_mode : 1;
   w.ok = true;
   return w;
 }

@@ -85,9 +85,11 @@ class BucketedAllReduce(object):
 
 class DataParallelTrainer(object):
     def __init__(self, net, lr=1e-3, optimizer="sgd", momentum=0.9, weight_decay=1e-4, clip_val=0.01, group=None,
-                 bucket_mb=4.0):
+                 bucket_mb=4.0, use_graph=False):
         if optimizer not in ("sgd", "adam"):
             raise ValueError("optimizer must be 'sgd' or 'adam'")
+        self.use_graph = use_graph
+        self.graph_launches = 0  # kernels launched through CUDA-graph replays (not seen by dards_launch_count)
         self.net, self.lr, self.optimizer = net, lr, optimizer
         self.momentum, self.weight_decay = momentum, weight_decay
         self.clip = float(clip_val) if clip_val else 0.0
@@ -139,17 +141,56 @@ class DataParallelTrainer(object):
         """x: this rank's (B_local, 20, 1, 224) on the device, target (B_local, 2).  Returns the device tensor
         holding the local mean loss (no host synchronisation)."""
         plan = self.plan_for(x)
-        st = plan._stream()
         plan.load_input(x)
+        t_static = plan.__dict__.get("_dp_target")
+        if t_static is None:
+            t_static = plan._dp_target = torch.empty((plan.logits.numel(),), dtype=torch.float32, device=self.device)
+        t_static.copy_(target.reshape(-1), non_blocking=True)
+        if self.use_graph and self.world == 1 and self.optimizer == "sgd":
+            return self._graphed_step(plan, t_static)
+        self._step_body(plan, t_static)
+        return self.loss_buf
+
+    def _step_body(self, plan, t_static):
+        st = plan._stream()
         plan.run_forward()
-        t = target if target.dtype == torch.float32 else target.float()
-        _lib.call("dards_bce_with_logits", plan.logits.data_ptr(), t.contiguous().data_ptr(), self.loss_buf.data_ptr(),
+        _lib.call("dards_bce_with_logits", plan.logits.data_ptr(), t_static.data_ptr(), self.loss_buf.data_ptr(),
                   plan.dlogits.data_ptr(), plan.logits.numel(), 1.0, st)
         if self.world > 1:
             self._backward_overlapped(plan)
         else:
             plan.run_backward()
         self._update(plan, st)
+
+    def _graphed_step(self, plan, t_static):
+        """Single-GPU SGD step as ONE CUDA-graph launch (weight packing, forward, loss, backward, update: ~200 kernel
+        launches otherwise issued from Python).  Captured lazily on the third call for a plan, after the eager warm-up
+        steps have initialised every lazily-set function attribute and the momentum buffers."""
+        st = plan.__dict__.setdefault("_dp_graph", {"calls": 0, "graph": None, "launches": 0})
+        if st["graph"] is not None:
+            st["graph"].replay()
+            self.step_count += 1
+            plan.fwd_serial += 1
+            plan.bwd_serial = plan.fwd_serial
+            self.graph_launches += st["launches"]
+            return self.loss_buf
+        st["calls"] += 1
+        if st["calls"] < 3 or self.step_count < 1:
+            self._step_body(plan, t_static)
+            return self.loss_buf
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.load().dards_launch_count()
+        with torch.cuda.graph(g):
+            plan._packed_version = None
+            self._step_body(plan, t_static)
+        st["launches"] = int(_lib.load().dards_launch_count() - l0)
+        st["graph"] = g
+        # capture does not execute: undo its bookkeeping, then run the step for real
+        self.step_count -= 1
+        g.replay()
+        self.step_count += 1
+        self.graph_launches += st["launches"]
         return self.loss_buf
 
     def _backward_overlapped(self, plan):

@@ -41,7 +41,7 @@ def test_argument_validation_returns_error_codes_not_crashes():
     rc = lib.dards_linear_fwd(16, 16, 16, 16, 1, 128, 99, None)
     assert rc == -1
     with pytest.raises(RuntimeError, match="deepards_b200"):
-        _lib.call("dards_stem_fwd", 16, 16, 16, 16, 16, 16, 16, 1, 20, 48, 48, 1e-5, 0, 0, None)  # C0 = 48 unsupported
+        _lib.call("dards_stem_fwd", 16, 16, 16, 16, 16, 16, 16, 1, 20, 40, 40, 1e-5, 0, 0, None)  # C0 = 40 unsupported
 
 
 @pytest.mark.parametrize("backbone", ["resnet18", "densenet18"])
