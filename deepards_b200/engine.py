@@ -84,6 +84,7 @@ class Plan(object):
         self.fwd = Recorder()
         self.bwd = Recorder()
         self.convs = []
+        self.sites = {}  # ReLU site name -> post-activation buffer (N, L, C); the parity tests read the decisions here
         self.bwd_marks = []  # (flat-gradient offset that is complete from there to the end, #bwd calls issued)
         self._scratch = {}
         self._packed_version = None
@@ -304,8 +305,8 @@ class Plan(object):
         stem_st = self._stem(m.conv1, m.bn1, pool, a.data_ptr(), c0)
         L = 56
         recs = []
-        for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
-            for blk in layer:
+        for li, layer in enumerate((m.layer1, m.layer2, m.layer3, m.layer4), 1):
+            for bi, blk in enumerate(layer):
                 r = {"blk": blk, "a_in": a, "l_in": L}
                 c1, c2 = self.conv(blk.conv1), self.conv(blk.conv2)
                 cin, cout = c1.cin, c1.cout
@@ -332,6 +333,8 @@ class Plan(object):
                 st2 = self.gbn_fwd(blk.bn2, y2.data_ptr(), cout, out.data_ptr(), cout, self.group * lo, cout, True,
                                    res=res.data_ptr(), res_stride=cout)
                 r.update(c1=c1, c2=c2, y1=y1, a1=a1, st1=st1, y2=y2, st2=st2, out=out, lo=lo, cin=cin, cout=cout)
+                self.sites["layer%d.%d.relu1" % (li, bi)] = a1
+                self.sites["layer%d.%d.relu2" % (li, bi)] = out
                 recs.append(r)
                 a, L = out, lo
         f = recs[-1]["cout"]
@@ -400,7 +403,7 @@ class Plan(object):
         for bi, (bname, block) in enumerate(blocks):
             lrecs = []
             cin = cin0
-            for layer in block.children():
+            for lname, layer in block.named_children():
                 c1, c2 = self.conv(layer.conv1), self.conv(layer.conv2)
                 mid, g = c1.cout, c2.cout
                 rows = self.group * L
@@ -418,6 +421,8 @@ class Plan(object):
                     seed = 0x5DEECE66D * drop_id + 11
                     self.fwd.add("dards_dropout", cat.data_ptr() + cin * esz, N * L, g, ctot, drop_p, seed,
                                  self.seed_dev.data_ptr(), self.dt)
+                self.sites["%s.%s.relu1" % (bname, lname)] = a
+                self.sites["%s.%s.relu2" % (bname, lname)] = b
                 lrecs.append(dict(layer=layer, c1=c1, c2=c2, a=a, st1=st1, y1=y1, b=b, st2=st2, cin=cin, mid=mid, g=g,
                                   seed=seed, drop_p=drop_p))
                 cin += g
@@ -438,6 +443,7 @@ class Plan(object):
                 ncat = self.new((N, L // 2, ntot), zero=True)
                 self.fwd.add("dards_avgpool2_fwd", y.data_ptr(), ncat.data_ptr(), N, L, ct.cout, ct.cout, ntot, self.dt)
                 br.update(trans=t, ct=ct, ta=a, tst=stt, ty=y)
+                self.sites["%s.relu" % tname] = a
                 brecs.append(br)
                 cat, ctot, L, cin0 = ncat, ntot, L // 2, ct.cout
             else:
@@ -457,6 +463,7 @@ class Plan(object):
             act = self.new((N, L, f))
             st5 = self.gbn_fwd(feats.norm5, cat.data_ptr(), ctot, act.data_ptr(), f, rows, f, True)
             self._head_fwd(act.data_ptr(), f, L, f)
+            self.sites["relu5"] = act
             d_act, relu5 = self.scratch("d_act", (N, L, f)), 1
             self._head_bwd(d_act.data_ptr(), f, L, f)
 

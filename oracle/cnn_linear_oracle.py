@@ -176,8 +176,31 @@ def _batchnorm(x, sd, name, running_update: bool):
     return y
 
 
+class DecisionHooks(object):
+    """Test instrumentation for the ReLU decisions (see tests/helpers.py, "pinned decisions").
+
+    record: {site: {sequence index: pre-activation tensor}} filled during the forward when not None.
+    masks : {site: bool tensor (B, N, C, L)}; where given, relu(z) is replaced by z * mask, i.e. the decision
+            "is this unit active" is taken from outside (from the implementation under test) instead of from
+            the sign of this run's own rounding noise.  Sites: "relu0" (stem, before the pool), "layerI.J.relu1",
+            "layerI.J.relu2", "denseblockI.denselayerJ.relu1|relu2", "transitionI.relu", "relu5"."""
+
+    def __init__(self, record=None, masks=None):
+        self.record, self.masks, self.seq = record, masks or {}, 0
+
+
+def _act(z, site, hooks):
+    if hooks is not None:
+        if hooks.record is not None:
+            hooks.record.setdefault(site, {})[hooks.seq] = z.detach()
+        m = hooks.masks.get(site)
+        if m is not None:
+            return z * m[hooks.seq].to(z.dtype)
+    return F.relu(z)
+
+
 def resnet_forward(sd, x, prefix: str = "", first_pool_type: str = "max", double_conv_first: bool = False,
-                   running_update: bool = False):
+                   running_update: bool = False, hooks=None):
     """(N, 1, 224) -> (N, 8*initial_planes); BN statistics over the whole N (resnet.py:141-163)."""
     g = lambda k: sd[prefix + k]
     bn = lambda t, name: _batchnorm(t, _Prefixed(sd, prefix), name, running_update)
@@ -189,7 +212,7 @@ def resnet_forward(sd, x, prefix: str = "", first_pool_type: str = "max", double
         y = bn(y, "bn1")
         y = F.conv1d(y, g("conv2.weight"), stride=2, padding=3)
         y = bn(y, "bn2")
-    y = F.relu(y)
+    y = _act(y, "relu0", hooks)
     if first_pool_type == "max":
         y = F.max_pool1d(y, 3, 2, 1)
     else:
@@ -201,7 +224,7 @@ def resnet_forward(sd, x, prefix: str = "", first_pool_type: str = "max", double
             pre = "layer%d.%d." % (li, bi)
             stride = 2 if (li > 1 and bi == 0) else 1
             out = F.conv1d(y, g(pre + "conv1.weight"), stride=stride, padding=1)
-            out = F.relu(bn(out, pre + "bn1"))
+            out = _act(bn(out, pre + "bn1"), pre + "relu1", hooks)
             out = F.conv1d(out, g(pre + "conv2.weight"), stride=1, padding=1)
             out = bn(out, pre + "bn2")
             if (prefix + pre + "downsample.0.weight") in sd:
@@ -209,7 +232,7 @@ def resnet_forward(sd, x, prefix: str = "", first_pool_type: str = "max", double
                 res = bn(res, pre + "downsample.1")
             else:
                 res = y
-            y = F.relu(out + res)
+            y = _act(out + res, pre + "relu2", hooks)
             bi += 1
         li += 1
     y = F.avg_pool1d(y, 7, 1)
@@ -233,22 +256,22 @@ class _Prefixed(dict):
         return self._b.get(self._p + k, default)
 
 
-def densenet_features(sd, x, prefix: str = "", drop_rate: float = 0.0, training: bool = False):
+def densenet_features(sd, x, prefix: str = "", drop_rate: float = 0.0, training: bool = False, hooks=None):
     """(N, C0, 224) -> (N, 128, 7): `DenseNet.features` (densenet.py:117-150).  BN always uses
     batch statistics (track_running_stats=False).  Dropout only if drop_rate>0 and training."""
     g = lambda k: sd[prefix + k]
     bn = lambda t, name: F.batch_norm(t, None, None, g(name + ".weight"), g(name + ".bias"), True, 0.0, BN_EPS)
     y = F.conv1d(x, g("features.conv0.weight"), stride=2, padding=3)
-    y = F.relu(bn(y, "features.norm0"))
+    y = _act(bn(y, "features.norm0"), "relu0", hooks)
     y = F.max_pool1d(y, 3, 2, 1)
     i = 1
     while (prefix + "features.denseblock%d.denselayer1.conv1.weight" % i) in sd:
         j = 1
         while (prefix + "features.denseblock%d.denselayer%d.conv1.weight" % (i, j)) in sd:
             pre = "features.denseblock%d.denselayer%d." % (i, j)
-            t = F.relu(bn(y, pre + "norm1"))
+            t = _act(bn(y, pre + "norm1"), pre[9:] + "relu1", hooks)
             t = F.conv1d(t, g(pre + "conv1.weight"))
-            t = F.relu(bn(t, pre + "norm2"))
+            t = _act(bn(t, pre + "norm2"), pre[9:] + "relu2", hooks)
             t = F.conv1d(t, g(pre + "conv2.weight"), padding=1)
             if drop_rate > 0:
                 t = F.dropout(t, p=drop_rate, training=training)
@@ -256,7 +279,7 @@ def densenet_features(sd, x, prefix: str = "", drop_rate: float = 0.0, training:
             j += 1
         pre = "features.transition%d." % i
         if (prefix + pre + "conv.weight") in sd:
-            t = F.relu(bn(y, pre + "norm"))
+            t = _act(bn(y, pre + "norm"), pre[9:] + "relu", hooks)
             t = F.conv1d(t, g(pre + "conv.weight"))
             y = F.avg_pool1d(t, 2, 2)
         i += 1
@@ -266,7 +289,7 @@ def densenet_features(sd, x, prefix: str = "", drop_rate: float = 0.0, training:
 def densenet_forward(sd, x, prefix: str = "", **kw):
     """densenet.py:179-189: relu(features) -> AvgPool1d(7) -> flatten."""
     f = densenet_features(sd, x, prefix, **kw)
-    y = F.avg_pool1d(F.relu(f), 7, 1)
+    y = F.avg_pool1d(_act(f, "relu5", kw.get("hooks")), 7, 1)
     return y.reshape(f.shape[0], -1)
 
 
@@ -286,6 +309,8 @@ def cnn_linear_forward(sd, x, per_breath: bool = False, **kw):
     w, b = sd["linear_final.weight"], sd["linear_final.bias"]
     rows = []
     for i in range(x.shape[0]):
+        if kw.get("hooks") is not None:
+            kw["hooks"].seq = i
         feat = backbone_forward(sd, x[i], **kw)
         if per_breath:
             rows.append(F.linear(feat, w, b).unsqueeze(0))

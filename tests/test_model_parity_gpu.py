@@ -17,8 +17,8 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from oracle import cnn_linear_oracle as O  # noqa: E402
-from tests.helpers import (CASES, conditioned_grad_check, cosine, golden_grad_errors, load_case,  # noqa: E402
-                           reference_sensitivity, rel_err)
+from tests.helpers import (CASES, cosine, golden_grad_errors, load_case, pinned_decision_check, plan_of,  # noqa: E402
+                           rel_err)
 
 FP32_TOL = 1e-4          # north_star: logits and gradients within 1e-4 relative error in fp32
 # bf16 storage + tcgen05 path (the "separately stated, looser tolerance" of the north_star).  bf16 rounding (2^-9)
@@ -71,14 +71,16 @@ def test_fp32_matches_reference_golden(name):
     errs = golden_grad_errors(z, grads)
     assert len(errs) > 10
     if max(errs.values()) > FP32_TOL:
-        # some tensor is off by more than 1e-4 from the recorded fp32 reference run: accept it only if the
-        # reference arithmetic is equally far from the exact gradient there (see conditioned_grad_check)
+        # some tensor is off by more than 1e-4 from the recorded fp32 reference run: that is only acceptable if a
+        # ReLU decision flipped at a near-tie -- prove it, and hold the arithmetic to 1e-4 with decisions pinned
         x, t = torch.from_numpy(z["x"]), torch.from_numpy(z["target"])
-        g32, g64, sens = reference_sensitivity(sd, x, t, per_breath=per_breath, **fkw)
-        worst, n_cond = conditioned_grad_check(grads, g32, g64, FP32_TOL, name, sens)
+        flips, worst = pinned_decision_check(plan_of(net, x.shape[0] * x.shape[1]), sd, x, t, grads, FP32_TOL, name,
+                                             per_breath=per_breath, **fkw)
+        assert flips > 0, "gradients differ from the golden run although every ReLU decision agrees"
     else:
-        worst, n_cond = max(errs.values()), 0
-    print("%s: worst strict grad rel err %.2e, tensors needing the conditioned clause: %d" % (name, worst, n_cond))
+        flips, worst = 0, max(errs.values())
+    print("%s: worst grad rel err %.2e (decisions pinned: %s, flipped near-tie decisions: %d)" %
+          (name, worst, flips > 0, flips))
     sd_after = net.state_dict()
     for key in z.files:
         if key.startswith("buf/"):
@@ -101,9 +103,10 @@ def test_fp32_matches_oracle_config1(backbone):
     out, loss, grads = step(net, x, t)
     assert rel_err(out, ref_out) <= FP32_TOL
     assert abs(loss - float(ref_loss)) <= FP32_TOL
-    _, g64, sens = reference_sensitivity(sd, x, t)
-    worst, n_cond = conditioned_grad_check(grads, ref_grads, g64, FP32_TOL, backbone, sens)
-    print("%s config1: worst strict grad rel err %.2e, conditioned tensors %d of %d" % (backbone, worst, n_cond, len(g64)))
+    flips, worst = pinned_decision_check(plan_of(net, 16 * 20), sd, x, t, grads, FP32_TOL, backbone)
+    raw = max(rel_err(grads[k].cpu(), g) for k, g in ref_grads.items())
+    print("%s config1: %d near-tie decisions flipped; worst grad rel err %.2e with decisions pinned (%.2e raw)" %
+          (backbone, flips, worst, raw))
     for k, g in grads.items():
         if k not in ref_grads:
             assert g is None, k  # conv1_alt / conv2 / bn2 never receive a gradient
