@@ -28,6 +28,47 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restri
   }
 }
 
+// All convolutions of a network in ONE launch: block b serves descriptor j with first_block[j] <= b < first_block[j+1]
+// and transposes one 32 (co) x 32 (ci) x ktaps tile through shared memory, so that the fp32 reads and both packed
+// writes are coalesced (a per-element scatter of 2-byte stores costs a 32-byte sector each).
+constexpr int PACK_TILE = 32;
+constexpr int PACK_MAX_TAPS = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) pack_conv_weights_batched_kernel(const dards_pack_desc* __restrict__ descs, int n) {
+  __shared__ dards_pack_desc d;
+  __shared__ float tile[PACK_TILE][PACK_TILE * PACK_MAX_TAPS + 1];
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < n && (int)blockIdx.x >= descs[j + 1].first_block) ++j;
+    d = descs[j];
+  }
+  __syncthreads();
+  const int K = d.ktaps, c_in = d.c_in, c_out = d.c_out;
+  const int n_co_t = (c_out + PACK_TILE - 1) / PACK_TILE;
+  const int b = (int)blockIdx.x - d.first_block;
+  const int co0 = (b % n_co_t) * PACK_TILE, ci0 = (b / n_co_t) * PACK_TILE;
+  const int row = PACK_TILE * K;  // floats of one co row inside the tile
+  for (int i = threadIdx.x; i < PACK_TILE * row; i += 256) {
+    const int co_l = i / row, rem = i % row;
+    const int co = co0 + co_l, ci = ci0 + rem / K;
+    tile[co_l][rem] = (co < c_out && ci < c_in) ? d.w[((size_t)co * c_in + ci0) * K + rem] : 0.f;
+  }
+  __syncthreads();
+  T* kio = static_cast<T*>(d.w_kio);
+  T* koi = static_cast<T*>(d.w_koi);
+  for (int i = threadIdx.x; i < PACK_TILE * PACK_TILE * K; i += 256) {
+    const int a = i % PACK_TILE, bq = (i / PACK_TILE) % PACK_TILE, t = i / (PACK_TILE * PACK_TILE);
+    if (koi) {  // a = ci (fastest in w_koi), bq = co
+      const int ci = ci0 + a, co = co0 + bq;
+      if (ci < c_in && co < c_out) Elem<T>::st(koi + ((size_t)t * c_out + co) * c_in + ci, tile[bq][a * K + t]);
+    }
+    if (kio) {  // a = co (fastest in w_kio), bq = ci
+      const int co = co0 + a, ci = ci0 + bq;
+      if (ci < c_in && co < c_out) Elem<T>::st(kio + ((size_t)t * c_in + ci) * c_out + co, tile[a][bq * K + t]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad implicit GEMM:  128 rows x 64 cols per CTA, BK = 16, 256 threads, 8x4 per thread
 // ------------------------------------------------------------------------------------------------
@@ -284,6 +325,13 @@ int simt_pack_conv_weight(const float* w, void* w_kio, void* w_koi, int c_out, i
                                                        ktaps);
   })
   DARDS_CHECK_LAUNCH("pack_conv_weight");
+  return DARDS_OK;
+}
+
+int simt_pack_conv_weights_batched(const dards_pack_desc* descs_dev, int n, int total_blocks, int dtype, cudaStream_t st) {
+  if (n == 0 || total_blocks == 0) return DARDS_OK;
+  DARDS_DISPATCH_DTYPE(dtype, { pack_conv_weights_batched_kernel<T><<<total_blocks, 256, 0, st>>>(descs_dev, n); })
+  DARDS_CHECK_LAUNCH("pack_conv_weights_batched");
   return DARDS_OK;
 }
 

@@ -146,19 +146,40 @@ __global__ void linear_bwd_data_kernel(const float* __restrict__ dlogits, const 
   }
 }
 
-// dw[j][k] (+)= sum_r dlogits[r][j] feat[r][k]  (thread per (j,k), rows in order -> deterministic)
-__global__ void linear_bwd_weight_kernel(const float* __restrict__ dlogits, const float* __restrict__ feat,
-                                         float* __restrict__ dw, float* __restrict__ db, int rows, int k, int n_out,
-                                         int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < k * n_out) {
-    int j = i / k, kk = i % k;
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s = fmaf(dlogits[(size_t)r * n_out + j], feat[(size_t)r * k + kk], s);
-    dw[i] = accumulate ? dw[i] + s : s;
+// dw[j][k] (+)= sum_r dlogits[r][j] feat[r][k].  256 threads = 64 columns k x 4 row lanes; every thread reads its
+// feat column once for all n_out outputs with 8 rows in flight; lane sums are combined in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256) linear_bwd_weight_kernel(const float* __restrict__ dlogits,
+                                                                const float* __restrict__ feat, float* __restrict__ dw,
+                                                                float* __restrict__ db, int rows, int k, int n_out,
+                                                                int accumulate) {
+  __shared__ float red[4][LIN_MAX_OUT][64];
+  const int col = threadIdx.x & 63, ln = threadIdx.x >> 6;
+  const int kk = blockIdx.x * 64 + col;
+  float acc[LIN_MAX_OUT];
+#pragma unroll
+  for (int j = 0; j < LIN_MAX_OUT; ++j) acc[j] = 0.f;
+  if (kk < k) {
+#pragma unroll 8
+    for (int r = ln; r < rows; r += 4) {
+      const float f = feat[(size_t)r * k + kk];
+#pragma unroll
+      for (int j = 0; j < LIN_MAX_OUT; ++j)
+        if (j < n_out) acc[j] = fmaf(dlogits[(size_t)r * n_out + j], f, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LIN_MAX_OUT; ++j) red[ln][j][col] = acc[j];
+  __syncthreads();
+  if (ln == 0 && kk < k) {
+    for (int j = 0; j < n_out; ++j) {
+      const float s = red[0][j][col] + red[1][j][col] + red[2][j][col] + red[3][j][col];
+      float* o = dw + (size_t)j * k + kk;
+      *o = accumulate ? *o + s : s;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < n_out && db) {
     float s = 0.f;
+#pragma unroll 8
     for (int r = 0; r < rows; ++r) s += dlogits[(size_t)r * n_out + threadIdx.x];
     db[threadIdx.x] = accumulate ? db[threadIdx.x] + s : s;
   }
@@ -273,8 +294,7 @@ int launch_linear_bwd(const float* dlogits, const float* feat, const float* w, f
     DARDS_CHECK_LAUNCH("linear_bwd_data");
   }
   if (dw) {
-    linear_bwd_weight_kernel<<<ceil_div((long long)k * n_out, 256), 256, 0, st>>>(dlogits, feat, dw, db, rows, k, n_out,
-                                                                                 accumulate);
+    linear_bwd_weight_kernel<<<ceil_div(k, 64), 256, 0, st>>>(dlogits, feat, dw, db, rows, k, n_out, accumulate);
     DARDS_CHECK_LAUNCH("linear_bwd_weight");
   }
   return DARDS_OK;

@@ -128,17 +128,42 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       const int k_steps = p.r_pad / 16;
+      // Descriptors are built ONCE: everything but the 14-bit start-address field is loop-invariant, and the
+      // start only moves by multiples of 16 bytes, so advancing is a single 64-bit add (the single issuing
+      // thread must spend far fewer than the ~64 cycles an MMA takes on each issue).
+      const uint64_t a_tmpl = make_sw128_desc(0, WG_CHUNK_A >> 4, 1024 >> 4, 1, 0);
+      uint64_t b_tmpl[WG_MAX_TAPS];
+      uint32_t d_tmem[WG_MAX_TAPS];
+#pragma unroll
+      for (int t = 0; t < WG_MAX_TAPS; ++t) {
+        const uint32_t off = WG_A_BYTES + p.tap_btile[t] * WG_B_BYTES + p.tap_shift[t] * 128;
+        const uint32_t bo = p.base_offset_mode == 0 ? (uint32_t)(p.tap_shift[t] & 7) : 0u;
+        b_tmpl[t] = make_sw128_desc(0, WG_CHUNK_B >> 4, 1024 >> 4, 1, bo) + (uint64_t)(off >> 4);
+        d_tmem[t] = tmem_base + (uint32_t)t * 128u;
+      }
+      const int n_taps = p.n_taps;
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * p.stage_bytes;
-        for (int kk = 0; kk < k_steps; ++kk) {
-          const uint64_t a_desc = make_sw128_desc(sa + kk * 2048, WG_CHUNK_A >> 4, 1024 >> 4, 1, 0);
-          for (int t = 0; t < p.n_taps; ++t) {
-            const uint32_t sb = sa + WG_A_BYTES + p.tap_btile[t] * WG_B_BYTES + kk * 2048 + p.tap_shift[t] * 128;
-            const uint32_t bo = p.base_offset_mode == 0 ? ((sb >> 7) & 7u) : 0u;
-            const uint64_t b_desc = make_sw128_desc(sb, WG_CHUNK_B >> 4, 1024 >> 4, 1, bo);
-            umma_bf16(tmem_base + (uint32_t)t * 128u, a_desc, b_desc, idesc, (it | kk) != 0 ? 1u : 0u);
+        const uint64_t sa16 = (uint64_t)((smem_base + stage * p.stage_bytes) >> 4);
+        uint64_t a_desc = a_tmpl + sa16;
+        uint64_t b0 = b_tmpl[0] + sa16, b1 = b_tmpl[1] + sa16, b2 = b_tmpl[2] + sa16;
+        uint32_t acc = it != 0 ? 1u : 0u;
+        if (n_taps == 3) {
+#pragma unroll 2
+          for (int kk = 0; kk < k_steps; ++kk) {
+            umma_bf16(d_tmem[0], a_desc, b0, idesc, acc);
+            umma_bf16(d_tmem[1], a_desc, b1, idesc, acc);
+            umma_bf16(d_tmem[2], a_desc, b2, idesc, acc);
+            a_desc += 128; b0 += 128; b1 += 128; b2 += 128;  // 16 reduction rows = 2048 bytes
+            acc = 1u;
+          }
+        } else {
+#pragma unroll 2
+          for (int kk = 0; kk < k_steps; ++kk) {
+            umma_bf16(d_tmem[0], a_desc, b0, idesc, acc);
+            a_desc += 128; b0 += 128;
+            acc = 1u;
           }
         }
         umma_commit(empty_bar(stage));
@@ -186,17 +211,36 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
   }
 }
 
-// dw[co][ci][t] (+)= sum_s partial[s][t][co][ci]
-__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int ktaps,
-                                       int c_in, int c_out, int accumulate) {
-  const int per = ktaps * c_in * c_out;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
-    // i indexes [t][co][ci] so that the reads are coalesced
-    const int ci = i % c_in, co = (i / c_in) % c_out, t = i / (c_in * c_out);
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(size_t)k * per + i];
-    const size_t o = ((size_t)co * c_in + ci) * ktaps + t;
-    dw[o] = accumulate ? dw[o] + s : s;
+// dw[co][ci][t] (+)= sum_s partial[s][t][co][ci].  256 threads = 32 float4 columns x 8 split lanes; every lane sums
+// its splits in order (4 loads in flight) and the 8 lane sums are combined in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                                              int splits, int ktaps, int c_in, int c_out, int accumulate) {
+  __shared__ float4 red[8][33];
+  const int per = ktaps * c_in * c_out;  // multiple of 4 (c_in % 16 == 0)
+  const int col = threadIdx.x & 31, ln = threadIdx.x >> 5;
+  const int i = (blockIdx.x * 32 + col) * 4;  // index into [t][co][ci], ci fastest
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < per) {
+#pragma unroll 4
+    for (int k = ln; k < splits; k += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * per + i));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  red[ln][col] = s;
+  __syncthreads();
+  if (ln == 0 && i < per) {
+    float4 t = red[0][col];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = red[k][col];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    const int ci = i % c_in, co = (i / c_in) % c_out, tap = i / (c_in * c_out);
+    float* o = dw + ((size_t)co * c_in + ci) * ktaps + tap;
+    const float r[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j * ktaps] = accumulate ? o[j * ktaps] + r[j] : r[j];
   }
 }
 
@@ -318,8 +362,7 @@ int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, v
   tc_wgrad_kernel<<<grid, WG_TC_THREADS, smem, st>>>(tm_a, tm_b, static_cast<float*>(workspace), p);
   DARDS_CHECK_LAUNCH("tc_wgrad");
   const int per = ktaps * c_in * c_out;
-  int blocks = ceil_div(per, 256);
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  const int blocks = ceil_div(per, 128);
   tc_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(workspace), dw, w.splits, ktaps, c_in, c_out,
                                                  accumulate);
   DARDS_CHECK_LAUNCH("tc_wgrad_reduce");

@@ -107,6 +107,7 @@ class Plan(object):
         # ---- I/O buffers ------------------------------------------------------------------------------------
         self.x_buf = self.new((n_breaths, SEQ_LEN), torch.float32)
         self.seed_dev = self.new((1,), torch.int64, zero=True)
+        self.counters = self.new((64,), torch.int32, zero=True)  # last-CTA tickets of the BN kernels (self-resetting)
         kind = backbone.network_name
         if kind.startswith("resnet"):
             self._build_resnet()
@@ -114,6 +115,7 @@ class Plan(object):
             self._build_densenet()
         else:
             raise NotImplementedError(kind)
+        self._build_pack_table()
 
     # ------------------------------------------------------------------------------------------------------
     # helpers
@@ -156,8 +158,6 @@ class Plan(object):
         c.stride, c.pad = mod.stride[0], mod.padding[0]
         c.kio = self.new((c.k, c.cin, c.cout))
         c.koi = self.new((c.k, c.cout, c.cin))
-        self.pack.add("dards_pack_conv_weight", mod.weight.data_ptr(), c.kio.data_ptr(), c.koi.data_ptr(), c.cout, c.cin,
-                      c.k, self.dt)
         self.convs.append(c)
         return c
 
@@ -208,18 +208,19 @@ class Plan(object):
 
     def gbn_fwd(self, bn, x, x_stride, out, out_stride, rows, c, relu, res=None, res_stride=0):
         mean, rstd = self.stats(c)
+        rm, rv, nbt, mom, cnt = self._running_args(bn)
         self.fwd.add("dards_gbn_fwd", x, out, res, bn.weight.data_ptr(), bn.bias.data_ptr(), mean.data_ptr(),
                      rstd.data_ptr(), self.G, rows, c, x_stride, out_stride, res_stride, BN_EPS, 1 if relu else 0,
-                     self.dt)
-        self._running(bn, mean, rstd, rows, c)
+                     rm, rv, nbt, mom, cnt, self.dt)
         return mean, rstd
 
-    def _running(self, bn, mean, rstd, rows, c):
+    def _running_args(self, bn):
+        """nn.BatchNorm1d running statistics: folded in by the last CTA of the BN launch (no extra kernel)."""
         if self.update_running and getattr(bn, "running_mean", None) is not None:
             nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
             mom = BN_MOMENTUM if bn.momentum is None else bn.momentum
-            self.fwd.add("dards_bn_running_update", mean.data_ptr(), rstd.data_ptr(), bn.running_mean.data_ptr(),
-                         bn.running_var.data_ptr(), nbt, self.G, rows, c, mom, BN_EPS)
+            return bn.running_mean.data_ptr(), bn.running_var.data_ptr(), nbt, mom, self.counters.data_ptr()
+        return None, None, None, BN_MOMENTUM, None
 
     def gbn_bwd(self, bn, st, dout, dout_stride, x, x_stride, dx, dx_stride, rows, c, relu_mode, mask=None,
                 mask_stride=0, accumulate=False, dres=None, dres_stride=0):
@@ -227,10 +228,9 @@ class Plan(object):
         dg = self.scratch("dgamma_part", (self.G, c), torch.float32)
         db = self.scratch("dbeta_part", (self.G, c), torch.float32)
         self.bwd.add("dards_gbn_bwd", dout, x, mask, bn.weight.data_ptr(), bn.bias.data_ptr(), mean.data_ptr(),
-                     rstd.data_ptr(), dx, 1 if accumulate else 0, dres, dg.data_ptr(), db.data_ptr(), self.G, rows, c,
+                     rstd.data_ptr(), dx, 1 if accumulate else 0, dres, dg.data_ptr(), db.data_ptr(),
+                     self.gptr(bn.weight), self.gptr(bn.bias), self.counters.data_ptr(), self.G, rows, c,
                      dout_stride, x_stride, mask_stride, dx_stride, dres_stride, relu_mode, self.dt)
-        self.bwd.add("dards_reduce_rows", dg.data_ptr(), self.gptr(bn.weight), self.G, c, 0)
-        self.bwd.add("dards_reduce_rows", db.data_ptr(), self.gptr(bn.bias), self.G, c, 0)
 
     # ------------------------------------------------------------------------------------------------------
     # stem (shared by both backbones)
@@ -240,10 +240,10 @@ class Plan(object):
         if conv.in_channels != 1 or conv.kernel_size[0] != 7 or conv.stride[0] != 2 or conv.padding[0] != 3:
             raise NotImplementedError("stem must be Conv1d(1, C0, 7, stride 2, padding 3)")
         mean, rstd = self.stats(c0)
+        rm, rv, nbt, mom, cnt = self._running_args(bn)
         self.fwd.add("dards_stem_fwd", self.x_buf.data_ptr(), conv.weight.data_ptr(), bn.weight.data_ptr(),
                      bn.bias.data_ptr(), out, mean.data_ptr(), rstd.data_ptr(), self.G, self.group, c0, out_stride,
-                     BN_EPS, pool, self.dt)
-        self._running(bn, mean, rstd, self.group * 112, c0)
+                     BN_EPS, pool, rm, rv, nbt, mom, cnt, self.dt)
         return mean, rstd
 
     def _stem_bwd(self, conv, bn, pool, st, dout, dout_stride):
@@ -254,10 +254,8 @@ class Plan(object):
         dbp = self.scratch("dbeta_part", (self.G, c0), torch.float32)
         self.bwd.add("dards_stem_bwd", dout, self.x_buf.data_ptr(), conv.weight.data_ptr(), bn.weight.data_ptr(),
                      bn.bias.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(),
+                     self.gptr(conv.weight), self.gptr(bn.weight), self.gptr(bn.bias), self.counters.data_ptr(),
                      self.G, self.group, c0, dout_stride, pool, self.dt)
-        self.bwd.add("dards_reduce_rows", dwp.data_ptr(), self.gptr(conv.weight), self.G, c0 * 7, 0)
-        self.bwd.add("dards_reduce_rows", dgp.data_ptr(), self.gptr(bn.weight), self.G, c0, 0)
-        self.bwd.add("dards_reduce_rows", dbp.data_ptr(), self.gptr(bn.bias), self.G, c0, 0)
 
     # ------------------------------------------------------------------------------------------------------
     # head
@@ -512,6 +510,21 @@ class Plan(object):
     # ------------------------------------------------------------------------------------------------------
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _build_pack_table(self):
+        """One `dards_pack_desc` per convolution, uploaded once: the whole network's weights are re-packed by a
+        single launch whenever they change."""
+        import numpy as np
+        dt = np.dtype([("w", "<u8"), ("kio", "<u8"), ("koi", "<u8"), ("c_out", "<i4"), ("c_in", "<i4"), ("ktaps", "<i4"),
+                       ("first_block", "<i4")])
+        tab = np.zeros(len(self.convs), dtype=dt)
+        first = 0
+        for i, c in enumerate(self.convs):
+            tab[i] = (c.mod.weight.data_ptr(), c.kio.data_ptr(), c.koi.data_ptr(), c.cout, c.cin, c.k, first)
+            first += ((c.cout + 31) // 32) * ((c.cin + 31) // 32)
+        self.pack_table = torch.from_numpy(tab.view(np.uint8).copy()).to(self.device)
+        self.bufs.append(self.pack_table)
+        self.pack.add("dards_pack_conv_weights_batched", self.pack_table.data_ptr(), len(self.convs), first, self.dt)
 
     def _pack_if_needed(self, st):
         ver = 0

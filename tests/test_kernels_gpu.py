@@ -249,6 +249,70 @@ def test_bn_running_update_matches_sequential_torch():
     assert int(nbt) == 3
 
 
+@pytest.mark.parametrize("n,c,l,group,dtype", [(120, 64, 14, 20, torch.float32), (5120, 128, 7, 20, torch.bfloat16),
+                                               (60, 96, 28, 20, torch.bfloat16)])
+def test_gbn_fused_running_stats_and_param_grad_reduction(n, c, l, group, dtype):
+    """The last-CTA reductions inside gbn_fwd / gbn_bwd equal the separate kernels (and torch's sequential update)."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(n, c, l, generator=g).to(DEV)
+    bn = torch.nn.BatchNorm1d(c).to(DEV).train()
+    for i in range(0, n, group):
+        bn(x[i:i + group].to(dtype).float())
+    gamma, beta = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    for rep in range(2):  # twice: the tickets must have reset themselves
+        rm.zero_(), rv.fill_(1.0), nbt.zero_()
+        out, mean, rstd = K().gbn_fwd(cl(x).to(dtype), gamma, beta, group * l, True, running=(rm, rv, nbt))
+        assert rel_err(rm, bn.running_mean) < 2e-5
+        assert rel_err(rv, bn.running_var) < 2e-5
+        assert int(nbt) == n // group
+    dy = torch.randn(n, l, c, generator=g).to(DEV).to(dtype)
+    a = K().gbn_bwd(dy, cl(x).to(dtype), gamma, beta, mean, rstd, group * l, 1, fused_reduce=True)
+    b = K().gbn_bwd(dy, cl(x).to(dtype), gamma, beta, mean, rstd, group * l, 1, fused_reduce=False)
+    assert torch.equal(a[0], b[0])
+    assert rel_err(a[1], b[1]) < 1e-6 and rel_err(a[2], b[2]) < 1e-6
+    a2 = K().gbn_bwd(dy, cl(x).to(dtype), gamma, beta, mean, rstd, group * l, 1, fused_reduce=True)
+    assert torch.equal(a[1], a2[1]) and torch.equal(a[2], a2[2])  # deterministic
+
+
+def test_stem_fused_running_stats_and_batched_pack():
+    from deepards_b200 import _lib
+    import numpy as np
+    n, c0, group = 100, 64, 20
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(n, 1, 224, generator=g).to(DEV)
+    w = (torch.randn(c0, 1, 7, generator=g) * 0.3).to(DEV)
+    bn = torch.nn.BatchNorm1d(c0).to(DEV).train()
+    for i in range(0, n, group):
+        bn(F.conv1d(x[i:i + group], w, stride=2, padding=3))
+    rm, rv = torch.zeros(c0, device=DEV), torch.ones(c0, device=DEV)
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    K().stem_fwd(x.view(n, 224), w, torch.ones(c0, device=DEV), torch.zeros(c0, device=DEV), group, 0, torch.float32,
+                 running=(rm, rv, nbt))
+    assert rel_err(rm, bn.running_mean) < 2e-5 and rel_err(rv, bn.running_var) < 2e-5 and int(nbt) == n // group
+    # batched weight packing == per-tensor packing
+    shapes = [(64, 64, 3), (128, 64, 1), (512, 256, 3), (32, 128, 3), (40, 24, 5)]
+    ws = [torch.randn(s, generator=g).to(DEV) for s in shapes]
+    dt = np.dtype([("w", "<u8"), ("kio", "<u8"), ("koi", "<u8"), ("c_out", "<i4"), ("c_in", "<i4"), ("ktaps", "<i4"),
+                   ("first_block", "<i4")])
+    tab = np.zeros(len(ws), dtype=dt)
+    outs, first = [], 0
+    for i, wt in enumerate(ws):
+        co, ci, k = wt.shape
+        kio = torch.zeros((k, ci, co), dtype=torch.bfloat16, device=DEV)
+        koi = torch.zeros((k, co, ci), dtype=torch.bfloat16, device=DEV)
+        outs.append((kio, koi))
+        tab[i] = (wt.data_ptr(), kio.data_ptr(), koi.data_ptr(), co, ci, k, first)
+        first += ((co + 31) // 32) * ((ci + 31) // 32)
+    tab_dev = torch.from_numpy(tab.view(np.uint8).copy()).to(DEV)
+    _lib.call("dards_pack_conv_weights_batched", tab_dev.data_ptr(), len(ws), first, _lib.BF16,
+              torch.cuda.current_stream().cuda_stream)
+    for wt, (kio, koi) in zip(ws, outs):
+        r_kio, r_koi = K().pack_conv_weight(wt, torch.bfloat16)
+        assert torch.equal(kio, r_kio) and torch.equal(koi, r_koi)
+
+
 @pytest.mark.parametrize("c0,group,pool", [(64, 20, 0), (16, 20, 0), (64, 20, 1), (32, 7, 0), (64, 60, 0)])
 def test_stem_forward_backward(c0, group, pool):
     n = group * 3

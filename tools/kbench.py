@@ -1,0 +1,149 @@
+"""Per-kernel CUDA-event timings at the BASELINE configs[1] layer shapes (N = 5120 breaths, bf16), L2-cold:
+every call works on one of ROT buffer sets (> 126 MB apart in total), so inputs come from HBM like inside a step.
+
+    python tools/kbench.py [bn] [conv] [wgrad] [stem]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from deepards_b200 import _lib  # noqa: E402
+
+DEV = "cuda"
+N, GROUP = 5120, 20
+SHAPES = [(64, 56), (128, 28), (256, 14), (512, 7)]
+ROT = 6
+BF = torch.bfloat16
+
+
+def timeit(fn, reps=18):
+    for i in range(ROT):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / reps
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bn():
+    G = N // GROUP
+    for c, l in SHAPES:
+        rows = GROUP * l
+        xs = [torch.randn(N, l, c, device=DEV).to(BF) for _ in range(ROT)]
+        gs = [torch.randn(N, l, c, device=DEV).to(BF) for _ in range(ROT)]
+        outs = [torch.empty(N, l, c, device=DEV, dtype=BF) for _ in range(ROT)]
+        out2 = [torch.empty(N, l, c, device=DEV, dtype=BF) for _ in range(ROT)]
+        gamma, beta = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+        mean, rstd = torch.empty(G, c, device=DEV), torch.empty(G, c, device=DEV)
+        dgp, dbp = torch.empty(G, c, device=DEV), torch.empty(G, c, device=DEV)
+        dg, db = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+        rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        nbt = torch.zeros((), dtype=torch.long, device=DEV)
+        cnt = torch.zeros(64, dtype=torch.int32, device=DEV)
+        mb = N * l * c * 2 / 1e6
+
+        def fwd(i, res=False, run=True):
+            k = i % ROT
+            _lib.call("dards_gbn_fwd", xs[k].data_ptr(), outs[k].data_ptr(), gs[k].data_ptr() if res else None,
+                      gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), G, rows, c, c, c, c, 1e-5, 1,
+                      rm.data_ptr() if run else None, rv.data_ptr() if run else None, nbt.data_ptr() if run else None,
+                      0.1, cnt.data_ptr() if run else None, _lib.BF16, st())
+
+        def bwd(i, mode=1, dres=False, fused=True):
+            k = i % ROT
+            _lib.call("dards_gbn_bwd", gs[k].data_ptr(), xs[k].data_ptr(), outs[k].data_ptr() if mode == 2 else None,
+                      gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), out2[k].data_ptr(), 0,
+                      gs[k].data_ptr() if dres else None, dgp.data_ptr(), dbp.data_ptr(),
+                      dg.data_ptr() if fused else None, db.data_ptr() if fused else None, cnt.data_ptr() if fused else None,
+                      G, rows, c, c, c, c, c, c, mode, _lib.BF16, st())
+
+        t = timeit(lambda i: fwd(i, False, False))
+        print("gbn_fwd  C=%3d L=%2d plain, no running : %6.1f us  %5.0f GB/s (r+w = %.0f MB)" % (c, l, t, 2 * mb / t * 1e-3 * 1e3, 2 * mb))
+        t = timeit(lambda i: fwd(i, False, True))
+        print("gbn_fwd  C=%3d L=%2d plain, running    : %6.1f us" % (c, l, t))
+        t = timeit(lambda i: fwd(i, True, True))
+        print("gbn_fwd  C=%3d L=%2d residual, running : %6.1f us  %5.0f GB/s" % (c, l, t, 3 * mb / t))
+        t = timeit(lambda i: bwd(i, 1, False, False))
+        print("gbn_bwd  C=%3d L=%2d mode1, unfused    : %6.1f us  %5.0f GB/s (2r+w)" % (c, l, t, 3 * mb / t))
+        t = timeit(lambda i: bwd(i, 1, False, True))
+        print("gbn_bwd  C=%3d L=%2d mode1, fused      : %6.1f us" % (c, l, t))
+        t = timeit(lambda i: bwd(i, 2, True, True))
+        print("gbn_bwd  C=%3d L=%2d mode2+dres, fused : %6.1f us  %5.0f GB/s (3r+2w)" % (c, l, t, 5 * mb / t), flush=True)
+
+
+def conv():
+    from deepards_b200 import kernels as K
+    for c, l in SHAPES:
+        xs = [torch.randn(N, l, c, device=DEV).to(BF) for _ in range(ROT)]
+        outs = [torch.empty(N, l, c, device=DEV, dtype=BF) for _ in range(ROT)]
+        w = torch.randn(c, c, 3, device=DEV) * 0.05
+        kio, koi = K.pack_conv_weight(w, BF)
+        fl = 2.0 * N * l * c * c * 3
+
+        def f(i):
+            k = i % ROT
+            _lib.call("dards_conv1d_fwd", xs[k].data_ptr(), koi.data_ptr(), outs[k].data_ptr(), None, N, l, l, c, c, c, c, 0,
+                      3, 1, 1, _lib.BF16, 1, st())
+
+        def d(i):
+            k = i % ROT
+            _lib.call("dards_conv1d_dgrad", xs[k].data_ptr(), kio.data_ptr(), outs[k].data_ptr(), None, N, l, l, c, c, c, c,
+                      0, 3, 1, 1, _lib.BF16, 1, st())
+
+        nb = _lib.fn("dards_conv1d_wgrad_workspace_bytes")(N, l, c, c, 3, 1)
+        ws = torch.empty(max(nb // 4, 1), device=DEV)
+        dw = torch.empty(c, c, 3, device=DEV)
+
+        def wg(i):
+            k = i % ROT
+            _lib.call("dards_conv1d_wgrad", xs[k].data_ptr(), outs[k].data_ptr(), dw.data_ptr(), 0, ws.data_ptr(),
+                      ws.numel() * 4, N, l, l, c, c, c, c, 3, 1, 1, _lib.BF16, 1, st())
+
+        for name, fn in (("fwd", f), ("dgrad", d), ("wgrad", wg)):
+            t = timeit(fn)
+            print("conv %-5s C=%3d L=%2d k3 s1: %6.1f us  %6.1f TFLOP/s" % (name, c, l, t, fl / t * 1e-6), flush=True)
+
+
+def stem():
+    G = N // GROUP
+    c0 = 64
+    xs = [torch.randn(N, 224, device=DEV) for _ in range(ROT)]
+    outs = [torch.empty(N, 56, c0, device=DEV, dtype=BF) for _ in range(ROT)]
+    w = torch.randn(c0, 1, 7, device=DEV) * 0.3
+    gamma, beta = torch.ones(c0, device=DEV), torch.zeros(c0, device=DEV)
+    mean, rstd = torch.empty(G, c0, device=DEV), torch.empty(G, c0, device=DEV)
+    dwp, dgp, dbp = torch.empty(G, c0 * 7, device=DEV), torch.empty(G, c0, device=DEV), torch.empty(G, c0, device=DEV)
+    dw, dg, db = torch.empty(c0 * 7, device=DEV), torch.empty(c0, device=DEV), torch.empty(c0, device=DEV)
+    cnt = torch.zeros(64, dtype=torch.int32, device=DEV)
+
+    def f(i):
+        k = i % ROT
+        _lib.call("dards_stem_fwd", xs[k].data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), outs[k].data_ptr(),
+                  mean.data_ptr(), rstd.data_ptr(), G, GROUP, c0, c0, 1e-5, 0, None, None, None, 0.1, None, _lib.BF16, st())
+
+    def b(i):
+        k = i % ROT
+        _lib.call("dards_stem_bwd", outs[k].data_ptr(), xs[k].data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                  mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(), dw.data_ptr(),
+                  dg.data_ptr(), db.data_ptr(), cnt.data_ptr(), G, GROUP, c0, c0, 0, _lib.BF16, st())
+
+    print("stem fwd: %6.1f us" % timeit(f))
+    print("stem bwd: %6.1f us" % timeit(b), flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["bn", "conv", "stem"]
+    torch.cuda.set_device(0)
+    _lib.load()
+    for wname in what:
+        {"bn": bn, "conv": conv, "stem": stem}[wname]()
