@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdeepards_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 P, I, LL, ULL, F = c_void_p, c_int, c_longlong, c_ulonglong, c_float
 
@@ -27,12 +27,14 @@ _SIGNATURES = {
     "dards_conv1d_dgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "dards_conv1d_wgrad": [P, P, P, I, P, LL, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "dards_conv1d_wgrad_workspace_bytes": [I, I, I, I, I, I],
-    "dards_gbn_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, P, P, P, F, P, I, P],
-    "dards_gbn_bwd": [P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
+    "dards_gbn_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, P],
+    "dards_gbn_bwd": [P, P, P, P, P, P, P, P, I, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "dards_reduce_rows": [P, P, I, I, I, P],
+    "dards_reduce_rows_batched": [P, I, I, P],
+    "dards_bn_running_update_batched": [P, I, I, F, P],
     "dards_bn_running_update": [P, P, P, P, P, I, I, I, F, F, P],
-    "dards_stem_fwd": [P, P, P, P, P, P, P, I, I, I, I, F, I, P, P, P, F, P, I, P],
-    "dards_stem_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "dards_stem_fwd": [P, P, P, P, P, P, P, I, I, I, I, F, I, I, P],
+    "dards_stem_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
     "dards_avgpool2_fwd": [P, P, I, I, I, I, I, I, P],
     "dards_avgpool2_bwd": [P, P, I, I, I, I, I, I, P],
     "dards_avgpool_full_fwd": [P, P, I, I, I, I, I, P],

@@ -39,18 +39,18 @@ long long tc_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out
 int tc_debug_set(int key, int value);
 
 int launch_gbn_fwd(const void*, void*, const void*, const float*, const float*, float*, float*, int, int, int, int, int,
-                   int, float, int, float*, float*, long long*, float, unsigned int*, int, cudaStream_t);
+                   int, float, int, int, cudaStream_t);
 int launch_gbn_bwd(const void*, const void*, const void*, const float*, const float*, const float*, const float*, void*,
-                   int, void*, float*, float*, float*, float*, unsigned int*, int, int, int, int, int, int, int, int, int,
-                   int, cudaStream_t);
+                   int, void*, float*, float*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int launch_reduce_rows_batched(const dards_reduce_desc*, int, int, cudaStream_t);
+int launch_bn_running_update_batched(const dards_running_desc*, int, int, float, cudaStream_t);
 int launch_reduce_rows(const float*, float*, int, int, int, cudaStream_t);
 int launch_bn_running_update(const float*, const float*, float*, float*, long long*, int, int, int, float, float,
                              cudaStream_t);
 int launch_stem_fwd(const float*, const float*, const float*, const float*, void*, float*, float*, int, int, int, int,
-                    float, int, float*, float*, long long*, float, unsigned int*, int, cudaStream_t);
+                    float, int, int, cudaStream_t);
 int launch_stem_bwd(const void*, const float*, const float*, const float*, const float*, const float*, const float*,
-                    float*, float*, float*, float*, float*, float*, unsigned int*, int, int, int, int, int, int,
-                    cudaStream_t);
+                    float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_avgpool2(int, const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int launch_avgpool_full_fwd(const void*, float*, int, int, int, int, int, cudaStream_t);
 int launch_avgpool_full_bwd(const float*, void*, int, int, int, int, int, cudaStream_t);
@@ -73,7 +73,7 @@ using namespace dards;
 
 extern "C" {
 
-int dards_version(void) { return 2; }
+int dards_version(void) { return 3; }
 
 const char* dards_last_error(void) { return g_err; }
 
@@ -176,30 +176,39 @@ long long dards_conv1d_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in,
 
 int dards_gbn_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta, float* save_mean,
                   float* save_rstd, int n_groups, int rows_per_group, int c, int x_stride, int out_stride,
-                  int res_stride, float eps, int relu, float* running_mean, float* running_var,
-                  long long* num_batches_tracked, float momentum, unsigned int* sync_counters, int dtype, void* stream) {
+                  int res_stride, float eps, int relu, int dtype, void* stream) {
   DARDS_CHECK_ARG(x && out && gamma && beta && save_mean && save_rstd, "gbn_fwd: null pointer");
   DARDS_CHECK_ARG(x_stride >= c && out_stride >= c, "gbn_fwd: row stride smaller than channel count");
   return launch_gbn_fwd(x, out, res, gamma, beta, save_mean, save_rstd, n_groups, rows_per_group, c, x_stride,
-                        out_stride, res_stride, eps, relu, running_mean, running_var, num_batches_tracked, momentum,
-                        sync_counters, dtype, S(stream));
+                        out_stride, res_stride, eps, relu, dtype, S(stream));
 }
 
 int dards_gbn_bwd(const void* dout, const void* x, const void* mask_src, const float* gamma, const float* beta,
                   const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
-                  float* dgamma_part, float* dbeta_part, float* dgamma, float* dbeta, unsigned int* sync_counters,
-                  int n_groups, int rows_per_group, int c, int dout_stride, int x_stride, int mask_stride,
-                  int dx_stride, int dres_stride, int relu_mode, int dtype, void* stream) {
+                  float* dgamma_part, float* dbeta_part, int n_groups, int rows_per_group, int c, int dout_stride,
+                  int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode, int dtype,
+                  void* stream) {
   DARDS_CHECK_ARG(dout && x && gamma && beta && save_mean && save_rstd && dx, "gbn_bwd: null pointer");
   DARDS_CHECK_ARG(relu_mode >= 0 && relu_mode <= 2, "gbn_bwd: relu_mode must be 0, 1 or 2");
   return launch_gbn_bwd(dout, x, mask_src, gamma, beta, save_mean, save_rstd, dx, accumulate_dx, dres, dgamma_part,
-                        dbeta_part, dgamma, dbeta, sync_counters, n_groups, rows_per_group, c, dout_stride, x_stride,
-                        mask_stride, dx_stride, dres_stride, relu_mode, dtype, S(stream));
+                        dbeta_part, n_groups, rows_per_group, c, dout_stride, x_stride, mask_stride, dx_stride,
+                        dres_stride, relu_mode, dtype, S(stream));
 }
 
 int dards_reduce_rows(const float* part, float* out, int rows, int c, int accumulate, void* stream) {
   DARDS_CHECK_ARG(part && out && rows >= 0 && c >= 0, "reduce_rows: bad argument");
   return launch_reduce_rows(part, out, rows, c, accumulate, S(stream));
+}
+
+int dards_reduce_rows_batched(const dards_reduce_desc* descs_dev, int n_descs, int total_blocks, void* stream) {
+  DARDS_CHECK_ARG(descs_dev && n_descs >= 0 && total_blocks >= 0, "reduce_rows_batched: bad argument");
+  return launch_reduce_rows_batched(descs_dev, n_descs, total_blocks, S(stream));
+}
+
+int dards_bn_running_update_batched(const dards_running_desc* descs_dev, int n_descs, int total_blocks, float eps,
+                                    void* stream) {
+  DARDS_CHECK_ARG(descs_dev && n_descs >= 0 && total_blocks >= 0, "bn_running_update_batched: bad argument");
+  return launch_bn_running_update_batched(descs_dev, n_descs, total_blocks, eps, S(stream));
 }
 
 int dards_bn_running_update(const float* save_mean, const float* save_rstd, float* running_mean, float* running_var,
@@ -211,25 +220,24 @@ int dards_bn_running_update(const float* save_mean, const float* save_rstd, floa
 }
 
 int dards_stem_fwd(const float* x, const float* w, const float* gamma, const float* beta, void* out, float* save_mean,
-                   float* save_rstd, int n_groups, int group, int c0, int out_stride, float eps, int pool,
-                   float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
-                   unsigned int* sync_counters, int dtype, void* stream) {
+                   float* save_rstd, int n_groups, int group, int c0, int out_stride, float eps, int pool, int dtype,
+                   void* stream) {
   DARDS_CHECK_ARG(x && w && gamma && beta && out && save_mean && save_rstd, "stem_fwd: null pointer");
   DARDS_CHECK_ARG(pool == 0 || pool == 1, "stem_fwd: pool must be 0 (max) or 1 (avg)");
   DARDS_CHECK_ARG(out_stride >= c0, "stem_fwd: row stride smaller than channel count");
-  return launch_stem_fwd(x, w, gamma, beta, out, save_mean, save_rstd, n_groups, group, c0, out_stride, eps, pool,
-                         running_mean, running_var, num_batches_tracked, momentum, sync_counters, dtype, S(stream));
+  return launch_stem_fwd(x, w, gamma, beta, out, save_mean, save_rstd, n_groups, group, c0, out_stride, eps, pool, dtype,
+                         S(stream));
 }
 
 int dards_stem_bwd(const void* dout, const float* x, const float* w, const float* gamma, const float* beta,
                    const float* save_mean, const float* save_rstd, float* dw_part, float* dgamma_part,
-                   float* dbeta_part, float* dw, float* dgamma, float* dbeta, unsigned int* sync_counters, int n_groups,
-                   int group, int c0, int dout_stride, int pool, int dtype, void* stream) {
+                   float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, int dtype,
+                   void* stream) {
   DARDS_CHECK_ARG(dout && x && w && gamma && beta && save_mean && save_rstd && dw_part && dgamma_part && dbeta_part,
                   "stem_bwd: null pointer");
   DARDS_CHECK_ARG(pool == 0 || pool == 1, "stem_bwd: pool must be 0 (max) or 1 (avg)");
-  return launch_stem_bwd(dout, x, w, gamma, beta, save_mean, save_rstd, dw_part, dgamma_part, dbeta_part, dw, dgamma,
-                         dbeta, sync_counters, n_groups, group, c0, dout_stride, pool, dtype, S(stream));
+  return launch_stem_bwd(dout, x, w, gamma, beta, save_mean, save_rstd, dw_part, dgamma_part, dbeta_part, n_groups, group,
+                         c0, dout_stride, pool, dtype, S(stream));
 }
 
 int dards_avgpool2_fwd(const void* in, void* out, int n_breaths, int l_in, int c, int in_stride, int out_stride,

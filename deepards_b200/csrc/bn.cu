@@ -1,26 +1,25 @@
 // Grouped BatchNorm1d (+residual, +ReLU) forward/backward on channels-last activations.
 //
-// Bandwidth-bound kernels: one CTA owns (one group of `rows` = group*L rows) x (8 x VEC channels), VEC = the
-// number of elements in a 16-byte access (4 fp32 / 8 bf16).  The group tile (<= 1120 x 128 bytes for a 20-breath
-// sequence) is streamed once from HBM and re-read from L1/L2 for the later sweeps.  Statistics use the
-// two-sweep (mean, then centred sum of squares) formulation for fp32-faithful variance.  Every sweep keeps
-// BN_UNROLL rows (16-byte loads of every operand) in flight per thread: the kernels are latency-bound otherwise.
+// Bandwidth-bound kernels.  One CTA owns (one group of `rows` = group*L rows) x (VPR 16-byte vectors of channels).
+// Two implementations of each direction:
 //
-// Cross-group reductions (running statistics in the forward; dgamma / dbeta in the backward) are done by the
-// LAST CTA to finish a channel tile (threadfence + atomic ticket, the counter resets itself): it reads the
-// per-group values written by all CTAs and reduces them in a fixed order, so the result is deterministic and
-// no extra kernel launch is needed.
+//  * cached (the fast path): the CTA's tile is read from global memory ONCE and parked in shared memory in a
+//    thread-private layout (cache[k][tid]: every thread only ever re-reads what it wrote, so there are no bank
+//    conflicts and no barriers around the cache); the later sweeps (centred variance, normalise / dx) run out of
+//    shared memory.  HBM/L2 traffic = the algorithmic minimum: fwd 1 read + 1 write, bwd 2 reads (+mask) + 1 write.
+//    The tile shape follows the layer: every ResNet-18 stage has rows*C = const, so (rows, channels per CTA) =
+//    (1120,32) (560,32) (280,64) (140,128) all give 9 rows per thread and a 72 KB tile per tensor.
+//  * streaming (generic fallback for tiles that do not fit): re-reads the tile from L1/L2 for every sweep.
 //
-// thread layout: 256 threads = 32 row lanes x 8 channel vectors.
+// Statistics use the two-sweep (mean, then centred sum of squares) formulation for fp32-faithful variance.
+// Cross-group reductions (running statistics, dgamma/dbeta) are separate BATCHED kernels: one launch handles a
+// whole table of BatchNorm layers (an in-kernel "last CTA reduces" variant was measured 12-19 us slower per launch:
+// the gpu-scope fence of every CTA invalidates L1 and waits for its stores).
 #include "common.cuh"
 
 namespace dards {
 
-constexpr int BN_THREADS = 256;
-constexpr int BN_LANES = 32;
-constexpr int BN_QUADS = 8;
-constexpr int BN_MAXCT = BN_QUADS * 8;  // 64 channels per CTA for bf16, 32 for fp32
-constexpr int BN_UNROLL = 4;
+constexpr int BN_UNROLL = 3;  // rows in flight per thread in the global-memory sweeps of the cached kernels
 
 template <typename T> struct Vec;
 template <> struct Vec<float> {
@@ -56,6 +55,280 @@ template <> struct Vec<__nv_bfloat16> {
 template <typename T> __device__ __forceinline__ uint4 ld16(const T* p) { return *reinterpret_cast<const uint4*>(p); }
 template <typename T> __device__ __forceinline__ void st16(T* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// =====================================================================================================
+// cached kernels
+// =====================================================================================================
+// Sum v[NV] over all threads of the CTA that share the channel vector cq = tid % VPR (i.e. over the row lanes);
+// every thread gets the totals of its own vector.  Warp shuffles over the row lanes inside a warp, then ONE thread
+// per value adds the warps' partial sums in a fixed order (deterministic) and broadcasts through shared memory --
+// this runs a few times per tile, so it must not cost every thread a loop over all warps.
+template <int NV, int VPR, int THREADS>
+__device__ __forceinline__ void rowlane_reduce(float (&v)[NV], float* red /* [THREADS/32 + 1][VPR*NV] */) {
+  constexpr int NW = THREADS / 32, W = VPR * NV;
+  static_assert(W <= THREADS, "one thread per reduced value");
+#pragma unroll
+  for (int off = VPR; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cq = threadIdx.x % VPR;
+  __syncthreads();  // previous use of `red` is over
+  if (lane < VPR) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) red[warp * W + lane * NV + j] = v[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < W) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += red[w * W + threadIdx.x];
+    red[NW * W + threadIdx.x] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = red[NW * W + cq * NV + j];
+}
+
+template <typename T, int VPR, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    gbn_fwd_cached_kernel(const T* x, T* out, const T* res, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float* __restrict__ save_mean, float* __restrict__ save_rstd, int rows, int c, int x_stride,
+                          int out_stride, int res_stride, float eps, int relu) {
+  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V, U = BN_UNROLL;
+  extern __shared__ uint4 cache[];  // [K][THREADS]
+  __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
+  const int g = blockIdx.y;
+  const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
+  const int c0 = blockIdx.x * CT + cq * V;
+  const bool active = c0 < c;
+  const size_t row_base = (size_t)g * rows;
+  const float inv_n = 1.f / (float)rows;
+  const int K = (rows + LANES - 1) / LANES;
+  const T* xp = x + row_base * x_stride + c0;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  // ---- sweep 1 (global): park the tile; shifted sums  sum(x - s), sum((x - s)^2)  with s = the group's first row.
+  // One pass with fp32-faithful variance: the shift is a sample of the data, so |mean - s| ~ std and the
+  // subtraction  E[d^2] - E[d]^2  cancels at most a digit (a plain sum of squares would lose |mean|^2/var). ----
+  float acc[2 * V], shift[V];
+#pragma unroll
+  for (int j = 0; j < 2 * V; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) shift[j] = 0.f;
+  if (active) {
+    Vec<T>::unpack(ld16(xp), shift);
+    for (int k0 = 0; k0 < K; k0 += U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rl + (k0 + u) * LANES;
+        raw[u] = r < rows ? ld16(xp + (size_t)r * x_stride) : zero4;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (rl + (k0 + u) * LANES < rows) {
+          cache[(k0 + u) * THREADS + threadIdx.x] = raw[u];
+          float v[V];
+          Vec<T>::unpack(raw[u], v);
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const float d = v[j] - shift[j];
+            acc[j] += d;
+            acc[V + j] = fmaf(d, d, acc[V + j]);
+          }
+        }
+      }
+    }
+  }
+  rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
+  if (!active) return;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float md = acc[j] * inv_n;  // mean - shift
+    const float var = fmaxf(fmaf(-md, md, acc[V + j] * inv_n), 0.f) + eps;
+    const float mean = shift[j] + md;
+    float rstd = rsqrtf(var);
+    rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);  // one Newton step: the reference divides by sqrt()
+    sc[j] = rstd * gamma[c0 + j];
+    sh[j] = beta[c0 + j] - mean * sc[j];
+    if (rl == 0) {
+      save_mean[(size_t)g * c + c0 + j] = mean;
+      save_rstd[(size_t)g * c + c0 + j] = rstd;
+    }
+  }
+  // ---- sweep 2 (shared -> global): normalise (+residual) (+ReLU) ----
+  T* op = out + row_base * out_stride + c0;
+  const T* rp = res ? res + row_base * res_stride + c0 : nullptr;
+  for (int k0 = 0; k0 < K; k0 += U) {
+    uint4 rres[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rl + (k0 + u) * LANES;
+      rres[u] = (rp && r < rows) ? ld16(rp + (size_t)r * res_stride) : zero4;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rl + (k0 + u) * LANES;
+      if (r < rows) {
+        float v[V];
+        Vec<T>::unpack(cache[(k0 + u) * THREADS + threadIdx.x], v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (rp) {
+          float e[V];
+          Vec<T>::unpack(rres[u], e);
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] += e[j];
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        st16(op + (size_t)r * out_stride, Vec<T>::pack(v));
+      }
+    }
+  }
+}
+
+template <typename T, int VPR, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    gbn_bwd_cached_kernel(const T* dout, const T* x, const T* mask_src, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ save_mean,
+                          const float* __restrict__ save_rstd, T* dx, int accumulate_dx, T* dres,
+                          float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int rows, int c, int dout_stride,
+                          int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode) {
+  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V, U = BN_UNROLL;
+  extern __shared__ uint4 cache[];  // [2][K][THREADS]: masked gradient, then x
+  __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
+  const int g = blockIdx.y;
+  const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
+  const int c0 = blockIdx.x * CT + cq * V;
+  const bool active = c0 < c;
+  const size_t row_base = (size_t)g * rows;
+  const float inv_n = 1.f / (float)rows;
+  const int K = (rows + LANES - 1) / LANES;
+  uint4* cache_g = cache;
+  uint4* cache_x = cache + (size_t)K * THREADS;
+  const T* gp = dout + row_base * dout_stride + c0;
+  const T* xp = x + row_base * x_stride + c0;
+  const T* mp = relu_mode == 2 ? mask_src + row_base * mask_stride + c0 : nullptr;
+  T* drp = dres ? dres + row_base * dres_stride + c0 : nullptr;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  float mean[V], rstd[V], sc[V], sh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    mean[j] = active ? save_mean[(size_t)g * c + c0 + j] : 0.f;
+    rstd[j] = active ? save_rstd[(size_t)g * c + c0 + j] : 0.f;
+    const float gm = active ? gamma[c0 + j] : 0.f, bt = active ? beta[c0 + j] : 0.f;
+    sc[j] = rstd[j] * gm;          // same arithmetic as the forward: y = fmaf(x, sc, sh)
+    sh[j] = bt - mean[j] * sc[j];
+  }
+
+  // ---- sweep 1 (global): mask the gradient, park (g, x), accumulate sum g and sum g*xhat ----
+  float acc[2 * V];
+#pragma unroll
+  for (int j = 0; j < 2 * V; ++j) acc[j] = 0.f;
+  if (active) {
+    for (int k0 = 0; k0 < K; k0 += U) {
+      uint4 rg[U], rx[U], rk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rl + (k0 + u) * LANES;
+        const bool ok = r < rows;
+        rg[u] = ok ? ld16(gp + (size_t)r * dout_stride) : zero4;
+        rx[u] = ok ? ld16(xp + (size_t)r * x_stride) : zero4;
+        rk[u] = (ok && mp) ? ld16(mp + (size_t)r * mask_stride) : zero4;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rl + (k0 + u) * LANES;
+        if (r < rows) {
+          float gv[V], xv[V];
+          Vec<T>::unpack(rg[u], gv);
+          Vec<T>::unpack(rx[u], xv);
+          if (relu_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              if (!(fmaf(xv[j], sc[j], sh[j]) > 0.f)) gv[j] = 0.f;
+          } else if (relu_mode == 2) {
+            float m[V];
+            Vec<T>::unpack(rk[u], m);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              if (!(m[j] > 0.f)) gv[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            acc[j] += gv[j];
+            acc[V + j] = fmaf(gv[j], xv[j] - mean[j], acc[V + j]);  // x rstd after the reduction
+          }
+          const uint4 pg = Vec<T>::pack(gv);  // exact: masking keeps or zeroes a value that already is a T
+          cache_g[(k0 + u) * THREADS + threadIdx.x] = pg;
+          cache_x[(k0 + u) * THREADS + threadIdx.x] = rx[u];
+          if (drp) st16(drp + (size_t)r * dres_stride, pg);
+        }
+      }
+    }
+  }
+  rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
+  if (!active) return;
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[V + j] *= rstd[j];
+  if (rl == 0) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      if (dbeta_part) dbeta_part[(size_t)g * c + c0 + j] = acc[j];
+      if (dgamma_part) dgamma_part[(size_t)g * c + c0 + j] = acc[V + j];
+    }
+  }
+  // dx = sc*(g - m1 - xhat*m2) = sc*g + kb*x + kc
+  float kb[V], kc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float m1 = acc[j] * inv_n, m2 = acc[V + j] * inv_n;
+    kb[j] = -sc[j] * m2 * rstd[j];
+    kc[j] = -sc[j] * m1 - kb[j] * mean[j];
+  }
+  // ---- sweep 2 (shared -> global) ----
+  T* dxp = dx + row_base * dx_stride + c0;
+  for (int k0 = 0; k0 < K; k0 += U) {
+    uint4 ro[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rl + (k0 + u) * LANES;
+      ro[u] = (accumulate_dx && r < rows) ? ld16(dxp + (size_t)r * dx_stride) : zero4;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rl + (k0 + u) * LANES;
+      if (r < rows) {
+        float gv[V], xv[V], o[V];
+        Vec<T>::unpack(cache_g[(k0 + u) * THREADS + threadIdx.x], gv);
+        Vec<T>::unpack(cache_x[(k0 + u) * THREADS + threadIdx.x], xv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(kb[j], xv[j], kc[j]));
+        if (accumulate_dx) {
+          float e[V];
+          Vec<T>::unpack(ro[u], e);
+#pragma unroll
+          for (int j = 0; j < V; ++j) o[j] += e[j];
+        }
+        st16(dxp + (size_t)r * dx_stride, Vec<T>::pack(o));
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// streaming kernels (generic fallback): 256 threads = 32 row lanes x 8 channel vectors
+// =====================================================================================================
+constexpr int BN_THREADS = 256;
+constexpr int BN_LANES = 32;
+constexpr int BN_QUADS = 8;
+constexpr int BN_MAXCT = BN_QUADS * 8;  // 64 channels per CTA for bf16, 32 for fp32
+
 // reduce v[V] over the 32 row lanes; the total for channel (cq*V + j) is returned to every thread of vector cq
 template <int V>
 __device__ __forceinline__ void lane_reduce(float (&v)[V], float (*red)[BN_MAXCT + 1], float* bcast, int rl, int cq) {
@@ -77,14 +350,11 @@ __device__ __forceinline__ void lane_reduce(float (&v)[V], float (*red)[BN_MAXCT
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
     gbn_fwd_kernel(const T* x, T* out, const T* res, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float* save_mean, float* save_rstd, int rows, int c, int x_stride, int out_stride, int res_stride,
-                   float eps, int relu, float* rm, float* rv, long long* nbt, float momentum, unsigned int* counters) {
+                   float* __restrict__ save_mean, float* __restrict__ save_rstd, int rows, int c, int x_stride,
+                   int out_stride, int res_stride, float eps, int relu) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = BN_UNROLL;
   __shared__ float red[BN_LANES][BN_MAXCT + 1];
   __shared__ float bcast[BN_MAXCT];
-  __shared__ int last_flag;
-  __shared__ float4 scratch4[BN_THREADS];
   const int g = blockIdx.y;
   const int rl = threadIdx.x >> 3, cq = threadIdx.x & 7;
   const int c0 = blockIdx.x * (BN_QUADS * V) + cq * V;
@@ -96,27 +366,13 @@ __global__ void __launch_bounds__(BN_THREADS)
   float s[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) s[j] = 0.f;
-  if (active) {
-    int r = rl;
-    for (; r + (U - 1) * BN_LANES < rows; r += U * BN_LANES) {
-      uint4 raw[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) raw[u] = ld16(xp + (size_t)(r + u * BN_LANES) * x_stride);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float v[V];
-        Vec<T>::unpack(raw[u], v);
-#pragma unroll
-        for (int j = 0; j < V; ++j) s[j] += v[j];
-      }
-    }
-    for (; r < rows; r += BN_LANES) {
+  if (active)
+    for (int r = rl; r < rows; r += BN_LANES) {
       float v[V];
       Vec<T>::unpack(ld16(xp + (size_t)r * x_stride), v);
 #pragma unroll
       for (int j = 0; j < V; ++j) s[j] += v[j];
     }
-  }
   lane_reduce<V>(s, red, bcast, rl, cq);
   float mean[V];
 #pragma unroll
@@ -125,24 +381,8 @@ __global__ void __launch_bounds__(BN_THREADS)
   float q[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) q[j] = 0.f;
-  if (active) {
-    int r = rl;
-    for (; r + (U - 1) * BN_LANES < rows; r += U * BN_LANES) {
-      uint4 raw[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) raw[u] = ld16(xp + (size_t)(r + u * BN_LANES) * x_stride);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float v[V];
-        Vec<T>::unpack(raw[u], v);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const float d = v[j] - mean[j];
-          q[j] = fmaf(d, d, q[j]);
-        }
-      }
-    }
-    for (; r < rows; r += BN_LANES) {
+  if (active)
+    for (int r = rl; r < rows; r += BN_LANES) {
       float v[V];
       Vec<T>::unpack(ld16(xp + (size_t)r * x_stride), v);
 #pragma unroll
@@ -151,82 +391,52 @@ __global__ void __launch_bounds__(BN_THREADS)
         q[j] = fmaf(d, d, q[j]);
       }
     }
-  }
   lane_reduce<V>(q, red, bcast, rl, cq);
+  if (!active) return;
   float sc[V], sh[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) sc[j] = sh[j] = 0.f;
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float var = q[j] * inv_n + eps;
-      float rstd = rsqrtf(var);
-      rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);  // one Newton step: the reference divides by sqrt()
-      sc[j] = rstd * gamma[c0 + j];
-      sh[j] = beta[c0 + j] - mean[j] * sc[j];
-      if (rl == 0) {
-        save_mean[(size_t)g * c + c0 + j] = mean[j];
-        save_rstd[(size_t)g * c + c0 + j] = rstd;
-      }
+  for (int j = 0; j < V; ++j) {
+    const float var = q[j] * inv_n + eps;
+    float rstd = rsqrtf(var);
+    rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);
+    sc[j] = rstd * gamma[c0 + j];
+    sh[j] = beta[c0 + j] - mean[j] * sc[j];
+    if (rl == 0) {
+      save_mean[(size_t)g * c + c0 + j] = mean[j];
+      save_rstd[(size_t)g * c + c0 + j] = rstd;
     }
   }
-  // running statistics: the last CTA of this channel tile to get here folds all groups' statistics in (before the
-  // output sweep, so the ticket's fence has no bulk stores to wait for)
-  if (rm != nullptr && last_cta_arrives(counters + blockIdx.x, gridDim.y, &last_flag)) {
-    const int ch0 = blockIdx.x * (BN_QUADS * V);
-    const int nch = (c - ch0) < BN_QUADS * V ? (c - ch0) : BN_QUADS * V;
-    running_update_tile(save_mean, save_rstd, rm, rv, gridDim.y, rows, c, ch0, nch, momentum, eps, scratch4);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += gridDim.y;
-  }
-  if (active) {
-    T* op = out + row_base * out_stride + c0;
-    const T* rp = res ? res + row_base * res_stride + c0 : nullptr;
-    auto finish = [&](const uint4& rx, const uint4& rr, int r) {
-      float v[V];
-      Vec<T>::unpack(rx, v);
+  T* op = out + row_base * out_stride + c0;
+  const T* rp = res ? res + row_base * res_stride + c0 : nullptr;
+  for (int r = rl; r < rows; r += BN_LANES) {
+    float v[V];
+    Vec<T>::unpack(ld16(xp + (size_t)r * x_stride), v);
 #pragma unroll
-      for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-      if (rp) {
-        float e[V];
-        Vec<T>::unpack(rr, e);
+    for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (rp) {
+      float e[V];
+      Vec<T>::unpack(ld16(rp + (size_t)r * res_stride), e);
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] += e[j];
-      }
-      if (relu) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      st16(op + (size_t)r * out_stride, Vec<T>::pack(v));
-    };
-    int r = rl;
-    for (; r + (U - 1) * BN_LANES < rows; r += U * BN_LANES) {
-      uint4 raw[U], rres[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        raw[u] = ld16(xp + (size_t)(r + u * BN_LANES) * x_stride);
-        rres[u] = rp ? ld16(rp + (size_t)(r + u * BN_LANES) * res_stride) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) finish(raw[u], rres[u], r + u * BN_LANES);
+      for (int j = 0; j < V; ++j) v[j] += e[j];
     }
-    for (; r < rows; r += BN_LANES)
-      finish(ld16(xp + (size_t)r * x_stride), rp ? ld16(rp + (size_t)r * res_stride) : make_uint4(0u, 0u, 0u, 0u), r);
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    st16(op + (size_t)r * out_stride, Vec<T>::pack(v));
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BN_THREADS, 2)
+__global__ void __launch_bounds__(BN_THREADS)
     gbn_bwd_kernel(const T* dout, const T* x, const T* mask_src, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
-                   T* dx, int accumulate_dx, T* dres, float* dgamma_part, float* dbeta_part, float* dgamma, float* dbeta,
-                   unsigned int* counters, int rows, int c, int dout_stride, int x_stride, int mask_stride, int dx_stride,
-                   int dres_stride, int relu_mode) {
+                   T* dx, int accumulate_dx, T* dres, float* __restrict__ dgamma_part, float* __restrict__ dbeta_part,
+                   int rows, int c, int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride,
+                   int relu_mode) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = BN_UNROLL;
   __shared__ float red[BN_LANES][BN_MAXCT + 1];
   __shared__ float bcast[BN_MAXCT];
-  __shared__ int last_flag;
-  __shared__ float4 scratch4[BN_THREADS];
   const int g = blockIdx.y;
   const int rl = threadIdx.x >> 3, cq = threadIdx.x & 7;
   const int c0 = blockIdx.x * (BN_QUADS * V) + cq * V;
@@ -243,126 +453,177 @@ __global__ void __launch_bounds__(BN_THREADS, 2)
     mean[j] = active ? save_mean[(size_t)g * c + c0 + j] : 0.f;
     rstd[j] = active ? save_rstd[(size_t)g * c + c0 + j] : 0.f;
     const float gm = active ? gamma[c0 + j] : 0.f, bt = active ? beta[c0 + j] : 0.f;
-    sc[j] = rstd[j] * gm;          // same arithmetic as the forward: y = fmaf(x, sc, sh)
+    sc[j] = rstd[j] * gm;
     sh[j] = bt - mean[j] * sc[j];
   }
-  // masked upstream gradient (gv) and the raw input (xv) of one row
-  auto decode = [&](const uint4& rg, const uint4& rx, const uint4& rm_, float (&gv)[V], float (&xv)[V]) {
-    Vec<T>::unpack(rg, gv);
-    Vec<T>::unpack(rx, xv);
+  auto load_row = [&](int r, float (&gv)[V], float (&xv)[V]) {
+    Vec<T>::unpack(ld16(gp + (size_t)r * dout_stride), gv);
+    Vec<T>::unpack(ld16(xp + (size_t)r * x_stride), xv);
     if (relu_mode == 1) {
 #pragma unroll
       for (int j = 0; j < V; ++j)
         if (!(fmaf(xv[j], sc[j], sh[j]) > 0.f)) gv[j] = 0.f;
     } else if (relu_mode == 2) {
       float m[V];
-      Vec<T>::unpack(rm_, m);
+      Vec<T>::unpack(ld16(mp + (size_t)r * mask_stride), m);
 #pragma unroll
       for (int j = 0; j < V; ++j)
         if (!(m[j] > 0.f)) gv[j] = 0.f;
     }
   };
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
   float s1[V], s2[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) s1[j] = s2[j] = 0.f;
-  if (active) {
-    auto acc = [&](const uint4& rg, const uint4& rx, const uint4& rm_) {
+  if (active)
+    for (int r = rl; r < rows; r += BN_LANES) {
       float gv[V], xv[V];
-      decode(rg, rx, rm_, gv, xv);
+      load_row(r, gv, xv);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         s1[j] += gv[j];
         s2[j] = fmaf(gv[j], (xv[j] - mean[j]) * rstd[j], s2[j]);
       }
-    };
-    int r = rl;
-    for (; r + (U - 1) * BN_LANES < rows; r += U * BN_LANES) {
-      uint4 rg[U], rx[U], rk[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const size_t rr = (size_t)(r + u * BN_LANES);
-        rg[u] = ld16(gp + rr * dout_stride);
-        rx[u] = ld16(xp + rr * x_stride);
-        rk[u] = mp ? ld16(mp + rr * mask_stride) : zero4;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) acc(rg[u], rx[u], rk[u]);
     }
-    for (; r < rows; r += BN_LANES)
-      acc(ld16(gp + (size_t)r * dout_stride), ld16(xp + (size_t)r * x_stride),
-          mp ? ld16(mp + (size_t)r * mask_stride) : zero4);
-  }
   lane_reduce<V>(s1, red, bcast, rl, cq);
   lane_reduce<V>(s2, red, bcast, rl, cq);
-  if (active && rl == 0) {
+  if (!active) return;
+  if (rl == 0) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       if (dbeta_part) dbeta_part[(size_t)g * c + c0 + j] = s1[j];
       if (dgamma_part) dgamma_part[(size_t)g * c + c0 + j] = s2[j];
     }
   }
-  // parameter gradients: the last CTA of this channel tile to get here sums the per-group partials in group order
-  // (before the dx sweep, so the ticket's fence has no bulk stores to wait for)
-  if (dgamma != nullptr && last_cta_arrives(counters + blockIdx.x, gridDim.y, &last_flag)) {
-    const int n_groups = gridDim.y;
-    const int ch0 = blockIdx.x * (BN_QUADS * V);
-    const int nch = (c - ch0) < BN_QUADS * V ? (c - ch0) : BN_QUADS * V;
-    auto one = [](int) { return 1.f; };
-    const float4 tg = group_reduce4(dgamma_part, n_groups, c, ch0, nch, one, scratch4);
-    const float4 tb = group_reduce4(dbeta_part, n_groups, c, ch0, nch, one, scratch4);
-    if (threadIdx.x < (nch >> 2)) {
-      reinterpret_cast<float4*>(dgamma + ch0)[threadIdx.x] = tg;
-      reinterpret_cast<float4*>(dbeta + ch0)[threadIdx.x] = tb;
-    }
+  float kb[V], kc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float m1 = s1[j] * inv_n, m2 = s2[j] * inv_n;
+    kb[j] = -sc[j] * m2 * rstd[j];
+    kc[j] = -sc[j] * m1 - kb[j] * mean[j];
   }
-  if (active) {
-    // dx = sc*(g - m1 - xhat*m2) = sc*g + kb*x + kc
-    float kb[V], kc[V];
+  T* dxp = dx + row_base * dx_stride + c0;
+  T* drp = dres ? dres + row_base * dres_stride + c0 : nullptr;
+  for (int r = rl; r < rows; r += BN_LANES) {
+    float gv[V], xv[V], o[V];
+    load_row(r, gv, xv);
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      const float m1 = s1[j] * inv_n, m2 = s2[j] * inv_n;
-      kb[j] = -sc[j] * m2 * rstd[j];
-      kc[j] = -sc[j] * m1 - kb[j] * mean[j];
+    for (int j = 0; j < V; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(kb[j], xv[j], kc[j]));
+    if (drp) st16(drp + (size_t)r * dres_stride, Vec<T>::pack(gv));
+    if (accumulate_dx) {
+      float e[V];
+      Vec<T>::unpack(ld16(dxp + (size_t)r * dx_stride), e);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] += e[j];
     }
-    T* dxp = dx + row_base * dx_stride + c0;
-    T* drp = dres ? dres + row_base * dres_stride + c0 : nullptr;
-    auto finish = [&](const uint4& rg, const uint4& rx, const uint4& rm_, const uint4& rold, int r) {
-      float gv[V], xv[V], o[V];
-      decode(rg, rx, rm_, gv, xv);
-#pragma unroll
-      for (int j = 0; j < V; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(kb[j], xv[j], kc[j]));
-      if (drp) st16(drp + (size_t)r * dres_stride, Vec<T>::pack(gv));
-      if (accumulate_dx) {
-        float e[V];
-        Vec<T>::unpack(rold, e);
-#pragma unroll
-        for (int j = 0; j < V; ++j) o[j] += e[j];
-      }
-      st16(dxp + (size_t)r * dx_stride, Vec<T>::pack(o));
-    };
-    int r = rl;
-    for (; r + (U - 1) * BN_LANES < rows; r += U * BN_LANES) {
-      uint4 rg[U], rx[U], rk[U], ro[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const size_t rr = (size_t)(r + u * BN_LANES);
-        rg[u] = ld16(gp + rr * dout_stride);
-        rx[u] = ld16(xp + rr * x_stride);
-        rk[u] = mp ? ld16(mp + rr * mask_stride) : zero4;
-        ro[u] = accumulate_dx ? ld16(dxp + rr * dx_stride) : zero4;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) finish(rg[u], rx[u], rk[u], ro[u], r + u * BN_LANES);
-    }
-    for (; r < rows; r += BN_LANES)
-      finish(ld16(gp + (size_t)r * dout_stride), ld16(xp + (size_t)r * x_stride),
-             mp ? ld16(mp + (size_t)r * mask_stride) : zero4, accumulate_dx ? ld16(dxp + (size_t)r * dx_stride) : zero4, r);
+    st16(dxp + (size_t)r * dx_stride, Vec<T>::pack(o));
   }
 }
 
-// out[i] (+)= sum_r part[r][i]: 256 threads = 32 columns x 8 row lanes, fixed summation order -> deterministic
+// =====================================================================================================
+// reductions over the groups
+// =====================================================================================================
+// One CTA (256 threads) reduces a [rows][c] fp32 table over the rows for 64 consecutive columns: threads = 16 float4
+// columns x 16 row lanes; every lane keeps 8 independent 16-byte loads in flight and the lane sums are combined in a
+// fixed order -> deterministic.  wfun(r) weights row r; tfun transforms a loaded value.
+template <typename WF, typename TF>
+__device__ __forceinline__ float4 table_reduce64(const float* __restrict__ table, int rows, int c, int col0, WF wfun,
+                                                 TF tfun, float4* scratch /* 256 */) {
+  const int col = threadIdx.x & 15, ln = threadIdx.x >> 4;
+  const int ch = col0 + col * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ch < c) {  // c % 4 == 0
+#pragma unroll 8
+    for (int r = ln; r < rows; r += 16) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(table + (size_t)r * c + ch));
+      const float w = wfun(r);
+      s.x = fmaf(w, tfun(v.x), s.x); s.y = fmaf(w, tfun(v.y), s.y);
+      s.z = fmaf(w, tfun(v.z), s.z); s.w = fmaf(w, tfun(v.w), s.w);
+    }
+  }
+  __syncthreads();
+  scratch[threadIdx.x] = s;
+  __syncthreads();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x < 16) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 v = scratch[k * 16 + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+  }
+  return t;  // valid in threads [0, 16): columns col0 + 4*threadIdx.x .. +3
+}
+
+// out[i] (+)= sum_r part[r][i] for a whole table of tensors in one launch
+__global__ void __launch_bounds__(256) reduce_rows_batched_kernel(const dards_reduce_desc* __restrict__ descs, int n) {
+  __shared__ dards_reduce_desc d;
+  __shared__ float4 scratch[256];
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < n && (int)blockIdx.x >= descs[j + 1].first_block) ++j;
+    d = descs[j];
+  }
+  __syncthreads();
+  const int col0 = ((int)blockIdx.x - d.first_block) * 64;
+  const float4 t = table_reduce64(d.part, d.rows, d.c, col0, [](int) { return 1.f; }, [](float v) { return v; }, scratch);
+  const int ch = col0 + threadIdx.x * 4;
+  if (threadIdx.x < 16 && ch < d.c) {
+    float4* o = reinterpret_cast<float4*>(d.out + ch);
+    float4 r = t;
+    if (d.accumulate) {
+      const float4 old = *o;
+      r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+    }
+    *o = r;
+  }
+}
+
+// nn.BatchNorm1d updates its running statistics once per group IN ORDER:  r <- (1-m) r + m v_g,  g = 0..G-1.
+// Closed form (SURVEY.md hard part 6):  r_G = (1-m)^G r_0 + m * sum_g (1-m)^(G-1-g) v_g  -- a weighted reduction.
+// The variance is recovered from the saved rstd: var_g = 1/rstd_g^2 - eps (biased) -> unbiased.
+__device__ __forceinline__ void running_update_block(const dards_running_desc& d, int col0, float eps, float4* scratch) {
+  const int n_groups = d.n_groups;
+  const float momentum = d.momentum;
+  const float unbias = d.rows_per_group > 1 ? (float)d.rows_per_group / (float)(d.rows_per_group - 1) : 1.f;
+  const float lg = log2f(1.f - momentum);
+  auto wfun = [&](int g) { return momentum * exp2f(lg * (float)(n_groups - 1 - g)); };
+  const float4 tm = table_reduce64(d.save_mean, n_groups, d.c, col0, wfun, [](float v) { return v; }, scratch);
+  const float4 tv = table_reduce64(d.save_rstd, n_groups, d.c, col0, wfun,
+                                   [&](float r) { return fmaxf(1.f / (r * r) - eps, 0.f) * unbias; }, scratch);
+  const int ch = col0 + threadIdx.x * 4;
+  if (threadIdx.x < 16 && ch < d.c) {
+    const float decay = exp2f(lg * (float)n_groups);
+    float4* pm = reinterpret_cast<float4*>(d.running_mean + ch);
+    float4* pv = reinterpret_cast<float4*>(d.running_var + ch);
+    float4 m = *pm, v = *pv;
+    m.x = decay * m.x + tm.x; m.y = decay * m.y + tm.y; m.z = decay * m.z + tm.z; m.w = decay * m.w + tm.w;
+    v.x = decay * v.x + tv.x; v.y = decay * v.y + tv.y; v.z = decay * v.z + tv.z; v.w = decay * v.w + tv.w;
+    *pm = m;
+    *pv = v;
+  }
+  if (col0 == 0 && threadIdx.x == 0 && d.num_batches_tracked) *d.num_batches_tracked += n_groups;
+}
+
+__global__ void __launch_bounds__(256) bn_running_update_batched_kernel(const dards_running_desc* __restrict__ descs, int n,
+                                                                        float eps) {
+  __shared__ dards_running_desc d;
+  __shared__ float4 scratch[256];
+  if (threadIdx.x == 0) {
+    int j = 0;
+    while (j + 1 < n && (int)blockIdx.x >= descs[j + 1].first_block) ++j;
+    d = descs[j];
+  }
+  __syncthreads();
+  running_update_block(d, ((int)blockIdx.x - d.first_block) * 64, eps, scratch);
+}
+
+__global__ void __launch_bounds__(256) bn_running_update_kernel(dards_running_desc d, float eps) {
+  __shared__ float4 scratch[256];
+  running_update_block(d, (int)blockIdx.x * 64, eps, scratch);
+}
+
+// single tensor: 256 threads = 32 columns x 8 row lanes (any c), fixed summation order -> deterministic
 constexpr int RR_LANES = 8;
 __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out,
                                                           int rows, int c, int accumulate) {
@@ -384,66 +645,141 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
   }
 }
 
-// stand-alone running-statistics update (the stem's BatchNorm; gbn_fwd does its own)
-__global__ void __launch_bounds__(BN_THREADS)
-    bn_running_update_kernel(const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
-                             float* __restrict__ rm, float* __restrict__ rv, long long* nbt, int n_groups, int rows, int c,
-                             float momentum, float eps) {
-  __shared__ float4 scratch[BN_THREADS];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += n_groups;
-  const int ch0 = blockIdx.x * 64;
-  const int nch = (c - ch0) < 64 ? (c - ch0) : 64;
-  running_update_tile(save_mean, save_rstd, rm, rv, n_groups, rows, c, ch0, nch, momentum, eps, scratch);
-}
-
 // ---- host launchers ------------------------------------------------------------------------------
 static int vec_of(int dtype) { return dtype == DARDS_BF16 ? 8 : 4; }
 
+// cached-kernel configurations: (threads, vectors per row) in order of preference for a given row count
+struct BnCfg { int threads, vpr; };
+static const BnCfg kBnCfgs[] = {{256, 16}, {256, 8}, {256, 4}, {512, 4}};
+constexpr int BN_MAX_K = 9;                 // rows per thread (bounds the cache: 9 * threads * 16 B per tensor)
+constexpr int BN_CACHE_LIMIT = 200 * 1024;  // dynamic shared memory we are willing to ask for
+
+// picks a configuration whose tile holds the whole group; -1 -> use the streaming kernels
+static int bn_pick_cfg(int rows, int c, int v, int tensors) {
+  for (int i = 0; i < 4; ++i) {
+    const int lanes = kBnCfgs[i].threads / kBnCfgs[i].vpr;
+    const int k = ceil_div(rows, lanes);
+    if (k > BN_MAX_K) continue;
+    if (i < 2 && kBnCfgs[i].vpr * v / 2 >= c) continue;  // tile at least twice as wide as the tensor
+    if ((long long)k * kBnCfgs[i].threads * 16 * tensors > BN_CACHE_LIMIT) continue;
+    return i;
+  }
+  return -1;
+}
+
+template <typename K>
+static int bn_smem_optin(K kernel, size_t smem, size_t* granted) {
+  if (smem <= *granted) return DARDS_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)  // the tiles are sized so that several CTAs share an SM: ask for all of the shared memory
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) {
+    set_error("gbn: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return DARDS_ERR_CUDA;
+  }
+  *granted = smem;
+  return DARDS_OK;
+}
+
+template <typename T, int VPR, int THREADS>
+static int run_fwd_cached(const void* x, void* out, const void* res, const float* gamma, const float* beta,
+                          float* save_mean, float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride,
+                          int res_stride, float eps, int relu, cudaStream_t st) {
+  static size_t granted = 32 * 1024;
+  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16;
+  int rc = bn_smem_optin(gbn_fwd_cached_kernel<T, VPR, THREADS>, smem, &granted);
+  if (rc) return rc;
+  dim3 grid(ceil_div(c, VPR * Vec<T>::N), n_groups);
+  gbn_fwd_cached_kernel<T, VPR, THREADS><<<grid, THREADS, smem, st>>>(
+      static_cast<const T*>(x), static_cast<T*>(out), static_cast<const T*>(res), gamma, beta, save_mean, save_rstd, rows, c,
+      x_stride, out_stride, res_stride, eps, relu);
+  return DARDS_OK;
+}
+
+template <typename T, int VPR, int THREADS>
+static int run_bwd_cached(const void* dout, const void* x, const void* mask_src, const float* gamma, const float* beta,
+                          const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
+                          float* dgamma_part, float* dbeta_part, int n_groups, int rows, int c, int dout_stride,
+                          int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode, cudaStream_t st) {
+  static size_t granted = 24 * 1024;
+  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16 * 2;
+  int rc = bn_smem_optin(gbn_bwd_cached_kernel<T, VPR, THREADS>, smem, &granted);
+  if (rc) return rc;
+  dim3 grid(ceil_div(c, VPR * Vec<T>::N), n_groups);
+  gbn_bwd_cached_kernel<T, VPR, THREADS><<<grid, THREADS, smem, st>>>(
+      static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,
+      save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, rows, c, dout_stride,
+      x_stride, mask_stride, dx_stride, dres_stride, relu_mode);
+  return DARDS_OK;
+}
+
+#define BN_DISPATCH_CFG(cfg, CALL)                                   \
+  switch (cfg) {                                                     \
+    case 0: { constexpr int VPR = 16, THREADS = 256; CALL; break; }  \
+    case 1: { constexpr int VPR = 8, THREADS = 256; CALL; break; }   \
+    case 2: { constexpr int VPR = 4, THREADS = 256; CALL; break; }   \
+    default: { constexpr int VPR = 4, THREADS = 512; CALL; break; }  \
+  }
+
 int launch_gbn_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta, float* save_mean,
                    float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride, int res_stride,
-                   float eps, int relu, float* rm, float* rv, long long* nbt, float momentum, unsigned int* counters,
-                   int dtype, cudaStream_t st) {
+                   float eps, int relu, int dtype, cudaStream_t st) {
   const int v = vec_of(dtype);
   DARDS_CHECK_ARG(c % v == 0 && x_stride % v == 0 && out_stride % v == 0 && (!res || res_stride % v == 0),
                   "gbn_fwd: channels and strides must be multiples of %d", v);
   DARDS_CHECK_ARG(rows > 0, "gbn_fwd: empty group");
-  DARDS_CHECK_ARG((rm == nullptr) == (rv == nullptr), "gbn_fwd: running_mean and running_var go together");
-  DARDS_CHECK_ARG(rm == nullptr || counters != nullptr, "gbn_fwd: the running-statistics update needs sync_counters");
   if (n_groups == 0) return DARDS_OK;
   DARDS_CHECK_ARG(n_groups <= 65535, "gbn_fwd: too many groups (%d)", n_groups);
-  dim3 grid(ceil_div(c, BN_QUADS * v), n_groups);
-  DARDS_DISPATCH_DTYPE(dtype, {
-    gbn_fwd_kernel<T><<<grid, BN_THREADS, 0, st>>>(static_cast<const T*>(x), static_cast<T*>(out),
-                                                   static_cast<const T*>(res), gamma, beta, save_mean, save_rstd, rows,
-                                                   c, x_stride, out_stride, res_stride, eps, relu, rm, rv, nbt, momentum,
-                                                   counters);
-  })
+  const int cfg = bn_pick_cfg(rows, c, v, 1);
+  if (cfg >= 0) {
+    int rc = DARDS_OK;
+    DARDS_DISPATCH_DTYPE(dtype, {
+      BN_DISPATCH_CFG(cfg, (rc = run_fwd_cached<T, VPR, THREADS>(x, out, res, gamma, beta, save_mean, save_rstd, n_groups, rows,
+                                                                 c, x_stride, out_stride, res_stride, eps, relu, st)));
+    })
+    if (rc) return rc;
+  } else {
+    dim3 grid(ceil_div(c, BN_QUADS * v), n_groups);
+    DARDS_DISPATCH_DTYPE(dtype, {
+      gbn_fwd_kernel<T><<<grid, BN_THREADS, 0, st>>>(static_cast<const T*>(x), static_cast<T*>(out),
+                                                     static_cast<const T*>(res), gamma, beta, save_mean, save_rstd, rows,
+                                                     c, x_stride, out_stride, res_stride, eps, relu);
+    })
+  }
   DARDS_CHECK_LAUNCH("gbn_fwd");
   return DARDS_OK;
 }
 
 int launch_gbn_bwd(const void* dout, const void* x, const void* mask_src, const float* gamma, const float* beta,
                    const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
-                   float* dgamma_part, float* dbeta_part, float* dgamma, float* dbeta, unsigned int* counters,
-                   int n_groups, int rows, int c, int dout_stride, int x_stride, int mask_stride, int dx_stride,
-                   int dres_stride, int relu_mode, int dtype, cudaStream_t st) {
+                   float* dgamma_part, float* dbeta_part, int n_groups, int rows, int c, int dout_stride, int x_stride,
+                   int mask_stride, int dx_stride, int dres_stride, int relu_mode, int dtype, cudaStream_t st) {
   const int v = vec_of(dtype);
   DARDS_CHECK_ARG(c % v == 0 && dout_stride % v == 0 && x_stride % v == 0 && dx_stride % v == 0,
                   "gbn_bwd: channels and strides must be multiples of %d", v);
   DARDS_CHECK_ARG(relu_mode != 2 || (mask_src && mask_stride % v == 0), "gbn_bwd: relu_mode 2 needs mask_src");
   DARDS_CHECK_ARG(!dres || dres_stride % v == 0, "gbn_bwd: dres stride");
-  DARDS_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "gbn_bwd: dgamma and dbeta go together");
-  DARDS_CHECK_ARG(dgamma == nullptr || (counters && dgamma_part && dbeta_part),
-                  "gbn_bwd: the fused dgamma/dbeta reduction needs the partial buffers and sync_counters");
   if (n_groups == 0) return DARDS_OK;
   DARDS_CHECK_ARG(n_groups <= 65535, "gbn_bwd: too many groups (%d)", n_groups);
-  dim3 grid(ceil_div(c, BN_QUADS * v), n_groups);
-  DARDS_DISPATCH_DTYPE(dtype, {
-    gbn_bwd_kernel<T><<<grid, BN_THREADS, 0, st>>>(
-        static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,
-        save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, dgamma, dbeta,
-        counters, rows, c, dout_stride, x_stride, mask_stride, dx_stride, dres_stride, relu_mode);
-  })
+  const int cfg = bn_pick_cfg(rows, c, v, 2);
+  if (cfg >= 0) {
+    int rc = DARDS_OK;
+    DARDS_DISPATCH_DTYPE(dtype, {
+      BN_DISPATCH_CFG(cfg, (rc = run_bwd_cached<T, VPR, THREADS>(dout, x, mask_src, gamma, beta, save_mean, save_rstd, dx,
+                                                                 accumulate_dx, dres, dgamma_part, dbeta_part, n_groups, rows,
+                                                                 c, dout_stride, x_stride, mask_stride, dx_stride,
+                                                                 dres_stride, relu_mode, st)));
+    })
+    if (rc) return rc;
+  } else {
+    dim3 grid(ceil_div(c, BN_QUADS * v), n_groups);
+    DARDS_DISPATCH_DTYPE(dtype, {
+      gbn_bwd_kernel<T><<<grid, BN_THREADS, 0, st>>>(
+          static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,
+          save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, rows, c,
+          dout_stride, x_stride, mask_stride, dx_stride, dres_stride, relu_mode);
+    })
+  }
   DARDS_CHECK_LAUNCH("gbn_bwd");
   return DARDS_OK;
 }
@@ -455,11 +791,30 @@ int launch_reduce_rows(const float* part, float* out, int rows, int c, int accum
   return DARDS_OK;
 }
 
+int launch_reduce_rows_batched(const dards_reduce_desc* descs_dev, int n, int total_blocks, cudaStream_t st) {
+  if (n == 0 || total_blocks == 0) return DARDS_OK;
+  reduce_rows_batched_kernel<<<total_blocks, 256, 0, st>>>(descs_dev, n);
+  DARDS_CHECK_LAUNCH("reduce_rows_batched");
+  return DARDS_OK;
+}
+
 int launch_bn_running_update(const float* save_mean, const float* save_rstd, float* rm, float* rv, long long* nbt,
                              int n_groups, int rows, int c, float momentum, float eps, cudaStream_t st) {
-  bn_running_update_kernel<<<ceil_div(c, 64), BN_THREADS, 0, st>>>(save_mean, save_rstd, rm, rv, nbt, n_groups, rows, c,
-                                                                   momentum, eps);
+  DARDS_CHECK_ARG(c % 4 == 0, "bn_running_update: channels must be a multiple of 4");
+  dards_running_desc d;
+  d.save_mean = save_mean; d.save_rstd = save_rstd; d.running_mean = rm; d.running_var = rv;
+  d.num_batches_tracked = nbt; d.n_groups = n_groups; d.rows_per_group = rows; d.c = c; d.momentum = momentum;
+  d.first_block = 0;
+  bn_running_update_kernel<<<ceil_div(c, 64), 256, 0, st>>>(d, eps);
   DARDS_CHECK_LAUNCH("bn_running_update");
+  return DARDS_OK;
+}
+
+int launch_bn_running_update_batched(const dards_running_desc* descs_dev, int n, int total_blocks, float eps,
+                                     cudaStream_t st) {
+  if (n == 0 || total_blocks == 0) return DARDS_OK;
+  bn_running_update_batched_kernel<<<total_blocks, 256, 0, st>>>(descs_dev, n, eps);
+  DARDS_CHECK_LAUNCH("bn_running_update_batched");
   return DARDS_OK;
 }
 

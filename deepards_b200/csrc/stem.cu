@@ -26,8 +26,6 @@ constexpr int STEM_BS = STEM_L + 2 * STEM_PAD;       // 240: smem breath stride 
 constexpr int STEM_RUN = 28;                         // conv outputs per run; 4 runs per breath
 constexpr int STEM_MAX_GROUP = 236;                  // 236 * 240 * 4 B = 226 KB of dynamic smem
 
-static_assert(STEM_THREADS == RED_THREADS, "last-CTA helpers assume 256 threads");
-
 // group input -> zero-padded shared copy
 __device__ __forceinline__ void stem_load_group(const float* __restrict__ xg, float* xs, int group) {
   for (int i = threadIdx.x; i < group * STEM_BS; i += STEM_THREADS) {
@@ -90,14 +88,11 @@ __device__ __forceinline__ void stem_tap_sums(const float* xs, int group, float*
 template <typename T>
 __global__ void __launch_bounds__(STEM_THREADS)
     stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, T* __restrict__ out, float* save_mean, float* save_rstd, int group,
-                    int c0, int out_stride, float eps, int pool, float* rm, float* rv, long long* nbt, float momentum,
-                    unsigned int* counters) {
+                    const float* __restrict__ beta, T* __restrict__ out, float* __restrict__ save_mean,
+                    float* __restrict__ save_rstd, int group, int c0, int out_stride, float eps, int pool) {
   extern __shared__ __align__(16) float xs[];
   __shared__ float red[STEM_THREADS];
   __shared__ float xt[STEM_K];
-  __shared__ int last_flag;
-  __shared__ float4 scratch4[STEM_THREADS];
   const int g = blockIdx.x;
   const int c = threadIdx.x % STEM_CS, rl = threadIdx.x / STEM_CS;
   const int ch = blockIdx.y * STEM_CS + c;  // c0 is a multiple of 16
@@ -136,12 +131,6 @@ __global__ void __launch_bounds__(STEM_THREADS)
     save_rstd[(size_t)g * c0 + ch] = rstd;
   }
   const float sc = rstd * gamma[ch], sh = beta[ch] - mean * sc;
-  // nn.BatchNorm1d running statistics: folded in by the last CTA of this channel slab to get here
-  if (rm != nullptr && last_cta_arrives(counters + blockIdx.y, gridDim.x, &last_flag)) {
-    running_update_tile(save_mean, save_rstd, rm, rv, gridDim.x, group * STEM_LC, c0, blockIdx.y * STEM_CS, STEM_CS,
-                        momentum, eps, scratch4);
-    if (blockIdx.y == 0 && threadIdx.x == 0 && nbt) *nbt += gridDim.x;
-  }
 
   // ---- sweep 2: conv + BN + ReLU + pool; run = 14 pool outputs = conv positions 2*lp0-1 .. 2*lp0+27 ----------
   for (int run = rl; run < n_runs; run += STEM_LANES) {
@@ -176,12 +165,11 @@ template <typename T>
 __global__ void __launch_bounds__(STEM_THREADS)
     stem_bwd_kernel(const T* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
-                    const float* __restrict__ save_rstd, float* dw_part, float* dgamma_part, float* dbeta_part, float* dw,
-                    float* dgamma, float* dbeta, unsigned int* counters, int group, int c0, int dout_stride, int pool) {
+                    const float* __restrict__ save_rstd, float* __restrict__ dw_part, float* __restrict__ dgamma_part,
+                    float* __restrict__ dbeta_part, int group, int c0, int dout_stride, int pool) {
   extern __shared__ __align__(16) float xs[];
-  __shared__ __align__(16) float red[STEM_THREADS * 9];
+  __shared__ float red[STEM_THREADS * 9];
   __shared__ float xr[STEM_K + STEM_NR];  // X_t (7) then R (28)
-  __shared__ int last_flag;
   const int g = blockIdx.x;
   const int tid = threadIdx.x;
   const int c = tid % STEM_CS, rl = tid / STEM_CS;
@@ -331,22 +319,6 @@ __global__ void __launch_bounds__(STEM_THREADS)
       dw_part[((size_t)g * c0 + ch) * STEM_K + t] = sc * (gt[t] - s1 * inv_n * xr[t] - s2 * inv_n * h);
     }
   }
-  if (dw == nullptr) return;
-  // parameter gradients: the last CTA of this channel slab sums the per-group partials in group order
-  if (!last_cta_arrives(counters + blockIdx.y, gridDim.x, &last_flag)) return;
-  {
-    float4* scratch4 = reinterpret_cast<float4*>(red);  // 256 float4 = 4 KB of the 9 KB array
-    const int n_groups = gridDim.x, ch0 = blockIdx.y * STEM_CS;
-    auto one = [](int) { return 1.f; };
-    const float4 tw = group_reduce4(dw_part, n_groups, c0 * STEM_K, ch0 * STEM_K, STEM_CS * STEM_K, one, scratch4);
-    if (tid < STEM_CS * STEM_K / 4) reinterpret_cast<float4*>(dw + ch0 * STEM_K)[tid] = tw;
-    const float4 tg = group_reduce4(dgamma_part, n_groups, c0, ch0, STEM_CS, one, scratch4);
-    const float4 tb = group_reduce4(dbeta_part, n_groups, c0, ch0, STEM_CS, one, scratch4);
-    if (tid < STEM_CS / 4) {
-      reinterpret_cast<float4*>(dgamma + ch0)[tid] = tg;
-      reinterpret_cast<float4*>(dbeta + ch0)[tid] = tb;
-    }
-  }
 }
 
 static bool stem_c0_ok(int c0) { return c0 > 0 && c0 % STEM_CS == 0; }
@@ -364,23 +336,21 @@ static int stem_smem_optin(K kernel, size_t smem, size_t* granted) {
 }
 
 int launch_stem_fwd(const float* x, const float* w, const float* gamma, const float* beta, void* out, float* save_mean,
-                    float* save_rstd, int n_groups, int group, int c0, int out_stride, float eps, int pool, float* rm,
-                    float* rv, long long* nbt, float momentum, unsigned int* counters, int dtype, cudaStream_t st) {
+                    float* save_rstd, int n_groups, int group, int c0, int out_stride, float eps, int pool, int dtype,
+                    cudaStream_t st) {
   DARDS_CHECK_ARG(stem_c0_ok(c0), "stem: initial planes must be a multiple of %d (got %d)", STEM_CS, c0);
   DARDS_CHECK_ARG(group > 0 && group <= STEM_MAX_GROUP, "stem: BatchNorm group must be in [1, %d] breaths (got %d)",
                   STEM_MAX_GROUP, group);
-  DARDS_CHECK_ARG((rm == nullptr) == (rv == nullptr), "stem_fwd: running_mean and running_var go together");
-  DARDS_CHECK_ARG(rm == nullptr || counters != nullptr, "stem_fwd: the running-statistics update needs sync_counters");
   if (n_groups == 0) return DARDS_OK;
   DARDS_CHECK_ARG(c0 / STEM_CS <= 65535, "stem: grid too large");
   const size_t smem = (size_t)group * STEM_BS * sizeof(float);
   dim3 grid(n_groups, c0 / STEM_CS);
-  static size_t granted[2] = {40 * 1024, 40 * 1024};  // 5.2 KB of static smem on top
+  static size_t granted[2] = {44 * 1024, 44 * 1024};  // 1 KB of static smem on top
   DARDS_DISPATCH_DTYPE(dtype, {
     int rc = stem_smem_optin(stem_fwd_kernel<T>, smem, &granted[dtype == DARDS_BF16 ? 1 : 0]);
     if (rc) return rc;
     stem_fwd_kernel<T><<<grid, STEM_THREADS, smem, st>>>(x, w, gamma, beta, static_cast<T*>(out), save_mean, save_rstd,
-                                                         group, c0, out_stride, eps, pool, rm, rv, nbt, momentum, counters);
+                                                         group, c0, out_stride, eps, pool);
   })
   DARDS_CHECK_LAUNCH("stem_fwd");
   return DARDS_OK;
@@ -388,14 +358,11 @@ int launch_stem_fwd(const float* x, const float* w, const float* gamma, const fl
 
 int launch_stem_bwd(const void* dout, const float* x, const float* w, const float* gamma, const float* beta,
                     const float* save_mean, const float* save_rstd, float* dw_part, float* dgamma_part,
-                    float* dbeta_part, float* dw, float* dgamma, float* dbeta, unsigned int* counters, int n_groups,
-                    int group, int c0, int dout_stride, int pool, int dtype, cudaStream_t st) {
+                    float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, int dtype,
+                    cudaStream_t st) {
   DARDS_CHECK_ARG(stem_c0_ok(c0), "stem: initial planes must be a multiple of %d (got %d)", STEM_CS, c0);
   DARDS_CHECK_ARG(group > 0 && group <= STEM_MAX_GROUP - 10, "stem: BatchNorm group must be in [1, %d] breaths (got %d)",
                   STEM_MAX_GROUP - 10, group);
-  DARDS_CHECK_ARG((dw == nullptr) == (dgamma == nullptr) && (dw == nullptr) == (dbeta == nullptr),
-                  "stem_bwd: dw, dgamma and dbeta go together");
-  DARDS_CHECK_ARG(dw == nullptr || counters != nullptr, "stem_bwd: the fused reduction needs sync_counters");
   if (n_groups == 0) return DARDS_OK;
   const size_t smem = (size_t)group * STEM_BS * sizeof(float);
   dim3 grid(n_groups, c0 / STEM_CS);
@@ -404,8 +371,8 @@ int launch_stem_bwd(const void* dout, const float* x, const float* w, const floa
     int rc = stem_smem_optin(stem_bwd_kernel<T>, smem, &granted[dtype == DARDS_BF16 ? 1 : 0]);
     if (rc) return rc;
     stem_bwd_kernel<T><<<grid, STEM_THREADS, smem, st>>>(static_cast<const T*>(dout), x, w, gamma, beta, save_mean,
-                                                         save_rstd, dw_part, dgamma_part, dbeta_part, dw, dgamma, dbeta,
-                                                         counters, group, c0, dout_stride, pool);
+                                                         save_rstd, dw_part, dgamma_part, dbeta_part, group, c0,
+                                                         dout_stride, pool);
   })
   DARDS_CHECK_LAUNCH("stem_bwd");
   return DARDS_OK;

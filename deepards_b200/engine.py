@@ -107,7 +107,8 @@ class Plan(object):
         # ---- I/O buffers ------------------------------------------------------------------------------------
         self.x_buf = self.new((n_breaths, SEQ_LEN), torch.float32)
         self.seed_dev = self.new((1,), torch.int64, zero=True)
-        self.counters = self.new((64,), torch.int32, zero=True)  # last-CTA tickets of the BN kernels (self-resetting)
+        self._running = []   # (mean, rstd, bn, rows, c): running-statistics updates, one batched launch per forward
+        self._pending_red = []  # (partial table, rows, c, destination pointer): flushed as one batched launch
         kind = backbone.network_name
         if kind.startswith("resnet"):
             self._build_resnet()
@@ -115,6 +116,8 @@ class Plan(object):
             self._build_densenet()
         else:
             raise NotImplementedError(kind)
+        self._flush_running()
+        self._flush_reductions()
         self._build_pack_table()
 
     # ------------------------------------------------------------------------------------------------------
@@ -144,6 +147,7 @@ class Plan(object):
     def mark(self, first_param):
         """Backward bookkeeping for the overlapped all-reduce: every gradient slot at or after `first_param`'s
         is final once the calls recorded so far have run (backward visits the layers last to first)."""
+        self._flush_reductions()
         self.bwd_marks.append((self.goff[id(first_param)], len(self.bwd.calls)))
 
     def grad_view(self, p):
@@ -208,29 +212,65 @@ class Plan(object):
 
     def gbn_fwd(self, bn, x, x_stride, out, out_stride, rows, c, relu, res=None, res_stride=0):
         mean, rstd = self.stats(c)
-        rm, rv, nbt, mom, cnt = self._running_args(bn)
         self.fwd.add("dards_gbn_fwd", x, out, res, bn.weight.data_ptr(), bn.bias.data_ptr(), mean.data_ptr(),
                      rstd.data_ptr(), self.G, rows, c, x_stride, out_stride, res_stride, BN_EPS, 1 if relu else 0,
-                     rm, rv, nbt, mom, cnt, self.dt)
+                     self.dt)
+        self._note_running(bn, mean, rstd, rows, c)
         return mean, rstd
 
-    def _running_args(self, bn):
-        """nn.BatchNorm1d running statistics: folded in by the last CTA of the BN launch (no extra kernel)."""
+    def _note_running(self, bn, mean, rstd, rows, c):
         if self.update_running and getattr(bn, "running_mean", None) is not None:
-            nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else None
+            self._running.append((mean, rstd, bn, rows, c))
+
+    def _flush_running(self):
+        """nn.BatchNorm1d running statistics of EVERY layer in one launch at the end of the forward (nothing in the
+        step reads them)."""
+        if not self._running:
+            return
+        import numpy as np
+        dt = np.dtype([("mean", "<u8"), ("rstd", "<u8"), ("rm", "<u8"), ("rv", "<u8"), ("nbt", "<u8"), ("n_groups", "<i4"),
+                       ("rows", "<i4"), ("c", "<i4"), ("momentum", "<f4"), ("first_block", "<i4"), ("reserved", "<i4")])
+        tab = np.zeros(len(self._running), dtype=dt)
+        first = 0
+        for i, (mean, rstd, bn, rows, c) in enumerate(self._running):
+            nbt = bn.num_batches_tracked.data_ptr() if bn.num_batches_tracked is not None else 0
             mom = BN_MOMENTUM if bn.momentum is None else bn.momentum
-            return bn.running_mean.data_ptr(), bn.running_var.data_ptr(), nbt, mom, self.counters.data_ptr()
-        return None, None, None, BN_MOMENTUM, None
+            tab[i] = (mean.data_ptr(), rstd.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(), nbt, self.G,
+                      rows, c, mom, first, 0)
+            first += (c + 63) // 64
+        t = torch.from_numpy(tab.view(np.uint8).copy()).to(self.device)
+        self.bufs.append(t)
+        self.fwd.add("dards_bn_running_update_batched", t.data_ptr(), len(self._running), first, BN_EPS)
+        self._running = []
+
+    def _flush_reductions(self):
+        """Per-group partial sums (BatchNorm dgamma/dbeta, stem dW) accumulated since the last flush -> their gradient
+        slots, in one launch."""
+        if not self._pending_red:
+            return
+        import numpy as np
+        dt = np.dtype([("part", "<u8"), ("out", "<u8"), ("rows", "<i4"), ("c", "<i4"), ("accumulate", "<i4"),
+                       ("first_block", "<i4")])
+        tab = np.zeros(len(self._pending_red), dtype=dt)
+        first = 0
+        for i, (part, rows, c, dst) in enumerate(self._pending_red):
+            tab[i] = (part.data_ptr(), dst, rows, c, 0, first)
+            first += (c + 63) // 64
+        t = torch.from_numpy(tab.view(np.uint8).copy()).to(self.device)
+        self.bufs.append(t)
+        self.bwd.add("dards_reduce_rows_batched", t.data_ptr(), len(self._pending_red), first)
+        self._pending_red = []
 
     def gbn_bwd(self, bn, st, dout, dout_stride, x, x_stride, dx, dx_stride, rows, c, relu_mode, mask=None,
                 mask_stride=0, accumulate=False, dres=None, dres_stride=0):
         mean, rstd = st
-        dg = self.scratch("dgamma_part", (self.G, c), torch.float32)
-        db = self.scratch("dbeta_part", (self.G, c), torch.float32)
+        dg = self.new((self.G, c), torch.float32)   # per layer: they live until the next flush
+        db = self.new((self.G, c), torch.float32)
         self.bwd.add("dards_gbn_bwd", dout, x, mask, bn.weight.data_ptr(), bn.bias.data_ptr(), mean.data_ptr(),
-                     rstd.data_ptr(), dx, 1 if accumulate else 0, dres, dg.data_ptr(), db.data_ptr(),
-                     self.gptr(bn.weight), self.gptr(bn.bias), self.counters.data_ptr(), self.G, rows, c,
+                     rstd.data_ptr(), dx, 1 if accumulate else 0, dres, dg.data_ptr(), db.data_ptr(), self.G, rows, c,
                      dout_stride, x_stride, mask_stride, dx_stride, dres_stride, relu_mode, self.dt)
+        self._pending_red.append((dg, self.G, c, self.gptr(bn.weight)))
+        self._pending_red.append((db, self.G, c, self.gptr(bn.bias)))
 
     # ------------------------------------------------------------------------------------------------------
     # stem (shared by both backbones)
@@ -240,22 +280,25 @@ class Plan(object):
         if conv.in_channels != 1 or conv.kernel_size[0] != 7 or conv.stride[0] != 2 or conv.padding[0] != 3:
             raise NotImplementedError("stem must be Conv1d(1, C0, 7, stride 2, padding 3)")
         mean, rstd = self.stats(c0)
-        rm, rv, nbt, mom, cnt = self._running_args(bn)
         self.fwd.add("dards_stem_fwd", self.x_buf.data_ptr(), conv.weight.data_ptr(), bn.weight.data_ptr(),
                      bn.bias.data_ptr(), out, mean.data_ptr(), rstd.data_ptr(), self.G, self.group, c0, out_stride,
-                     BN_EPS, pool, rm, rv, nbt, mom, cnt, self.dt)
+                     BN_EPS, pool, self.dt)
+        self._note_running(bn, mean, rstd, self.group * 112, c0)
         return mean, rstd
 
     def _stem_bwd(self, conv, bn, pool, st, dout, dout_stride):
         c0 = conv.out_channels
         mean, rstd = st
-        dwp = self.scratch("stem_dw_part", (self.G, c0 * 7), torch.float32)
-        dgp = self.scratch("dgamma_part", (self.G, c0), torch.float32)
-        dbp = self.scratch("dbeta_part", (self.G, c0), torch.float32)
+        dwp = self.new((self.G, c0 * 7), torch.float32)
+        dgp = self.new((self.G, c0), torch.float32)
+        dbp = self.new((self.G, c0), torch.float32)
         self.bwd.add("dards_stem_bwd", dout, self.x_buf.data_ptr(), conv.weight.data_ptr(), bn.weight.data_ptr(),
                      bn.bias.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(),
-                     self.gptr(conv.weight), self.gptr(bn.weight), self.gptr(bn.bias), self.counters.data_ptr(),
                      self.G, self.group, c0, dout_stride, pool, self.dt)
+        self._pending_red.append((dwp, self.G, c0 * 7, self.gptr(conv.weight)))
+        self._pending_red.append((dgp, self.G, c0, self.gptr(bn.weight)))
+        self._pending_red.append((dbp, self.G, c0, self.gptr(bn.bias)))
+        self._flush_reductions()
 
     # ------------------------------------------------------------------------------------------------------
     # head

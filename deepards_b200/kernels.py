@@ -74,13 +74,8 @@ def conv1d_wgrad(x, dout, k, stride, pad, impl=0):
     return dw
 
 
-def _counters(dev):
-    return torch.zeros((64,), dtype=torch.int32, device=dev)
-
-
-def gbn_fwd(x, gamma, beta, group_rows, relu, res=None, eps=1e-5, running=None, momentum=0.1):
-    """x (N, L, C); statistics over `group_rows` consecutive rows of the flattened (N*L, C) view.
-    running = (running_mean, running_var, num_batches_tracked) is updated in place when given."""
+def gbn_fwd(x, gamma, beta, group_rows, relu, res=None, eps=1e-5):
+    """x (N, L, C); statistics over `group_rows` consecutive rows of the flattened (N*L, C) view."""
     n, l, c = x.shape
     g = (n * l) // group_rows
     out = torch.empty((n, l, c), dtype=x.dtype, device=x.device)
@@ -88,36 +83,30 @@ def gbn_fwd(x, gamma, beta, group_rows, relu, res=None, eps=1e-5, running=None, 
     rstd = torch.empty((g, c), dtype=torch.float32, device=x.device)
     _lib.call("dards_gbn_fwd", x.data_ptr(), out.data_ptr(), res.data_ptr() if res is not None else None,
               gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g, group_rows, c, _rowstride(x),
-              _rowstride(out), _rowstride(res) if res is not None else 0, eps, 1 if relu else 0,
-              running[0].data_ptr() if running else None, running[1].data_ptr() if running else None,
-              running[2].data_ptr() if running and running[2] is not None else None, momentum,
-              _counters(x.device).data_ptr() if running else None, _dt(x), _st(x))
+              _rowstride(out), _rowstride(res) if res is not None else 0, eps, 1 if relu else 0, _dt(x), _st(x))
     return out, mean, rstd
 
 
-def gbn_bwd(dout, x, gamma, beta, mean, rstd, group_rows, relu_mode, mask_src=None, want_dres=False, fused_reduce=True):
+def gbn_bwd(dout, x, gamma, beta, mean, rstd, group_rows, relu_mode, mask_src=None, want_dres=False):
     n, l, c = x.shape
     g = (n * l) // group_rows
     dx = torch.empty((n, l, c), dtype=x.dtype, device=x.device)
     dres = torch.empty_like(dx) if want_dres else None
     dgp = torch.empty((g, c), dtype=torch.float32, device=x.device)
     dbp = torch.empty((g, c), dtype=torch.float32, device=x.device)
-    dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
-    dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
     _lib.call("dards_gbn_bwd", dout.data_ptr(), x.data_ptr(), mask_src.data_ptr() if mask_src is not None else None,
               gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), 0,
-              dres.data_ptr() if dres is not None else None, dgp.data_ptr(), dbp.data_ptr(),
-              dgamma.data_ptr() if fused_reduce else None, dbeta.data_ptr() if fused_reduce else None,
-              _counters(x.device).data_ptr() if fused_reduce else None, g, group_rows, c,
+              dres.data_ptr() if dres is not None else None, dgp.data_ptr(), dbp.data_ptr(), g, group_rows, c,
               _rowstride(dout), _rowstride(x), _rowstride(mask_src) if mask_src is not None else 0, _rowstride(dx),
               _rowstride(dres) if dres is not None else 0, relu_mode, _dt(x), _st(x))
-    if not fused_reduce:
-        _lib.call("dards_reduce_rows", dgp.data_ptr(), dgamma.data_ptr(), g, c, 0, _st(x))
-        _lib.call("dards_reduce_rows", dbp.data_ptr(), dbeta.data_ptr(), g, c, 0, _st(x))
+    dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
+    dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
+    _lib.call("dards_reduce_rows", dgp.data_ptr(), dgamma.data_ptr(), g, c, 0, _st(x))
+    _lib.call("dards_reduce_rows", dbp.data_ptr(), dbeta.data_ptr(), g, c, 0, _st(x))
     return dx, dgamma, dbeta, dres
 
 
-def stem_fwd(x, w, gamma, beta, group, pool, dtype, eps=1e-5, running=None, momentum=0.1):
+def stem_fwd(x, w, gamma, beta, group, pool, dtype, eps=1e-5):
     """x (N, 224) fp32 -> (N, 56, C0) in `dtype`, plus per-group mean / rstd."""
     n = x.shape[0]
     c0 = w.shape[0]
@@ -126,14 +115,11 @@ def stem_fwd(x, w, gamma, beta, group, pool, dtype, eps=1e-5, running=None, mome
     mean = torch.empty((g, c0), dtype=torch.float32, device=x.device)
     rstd = torch.empty((g, c0), dtype=torch.float32, device=x.device)
     _lib.call("dards_stem_fwd", x.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-              mean.data_ptr(), rstd.data_ptr(), g, group, c0, c0, eps, pool,
-              running[0].data_ptr() if running else None, running[1].data_ptr() if running else None,
-              running[2].data_ptr() if running and running[2] is not None else None, momentum,
-              _counters(x.device).data_ptr() if running else None, _DT[dtype], _st(x))
+              mean.data_ptr(), rstd.data_ptr(), g, group, c0, c0, eps, pool, _DT[dtype], _st(x))
     return out, mean, rstd
 
 
-def stem_bwd(dout, x, w, gamma, beta, mean, rstd, group, pool, fused_reduce=True):
+def stem_bwd(dout, x, w, gamma, beta, mean, rstd, group, pool):
     n = x.shape[0]
     c0 = w.shape[0]
     g = n // group
@@ -141,16 +127,9 @@ def stem_bwd(dout, x, w, gamma, beta, mean, rstd, group, pool, fused_reduce=True
     dwp = torch.empty((g, c0 * 7), dtype=torch.float32, device=dev)
     dgp = torch.empty((g, c0), dtype=torch.float32, device=dev)
     dbp = torch.empty((g, c0), dtype=torch.float32, device=dev)
-    dw = torch.empty((c0, 1, 7), dtype=torch.float32, device=dev)
-    dg = torch.empty((c0,), dtype=torch.float32, device=dev)
-    db = torch.empty((c0,), dtype=torch.float32, device=dev)
     _lib.call("dards_stem_bwd", dout.data_ptr(), x.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-              mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(),
-              dw.data_ptr() if fused_reduce else None, dg.data_ptr() if fused_reduce else None,
-              db.data_ptr() if fused_reduce else None, _counters(dev).data_ptr() if fused_reduce else None, g, group, c0,
+              mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(), g, group, c0,
               _rowstride(dout), pool, _dt(dout), _st(x))
-    if fused_reduce:
-        return dw, dg, db
     return dwp.sum(0).view(c0, 1, 7), dgp.sum(0), dbp.sum(0)
 
 

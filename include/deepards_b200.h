@@ -102,53 +102,63 @@ long long dards_conv1d_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in,
 /* Training-mode nn.BatchNorm1d over groups of `rows_per_group` = group*L rows: biased variance, eps;
  * out = [relu]( (x-mean)*rstd*gamma + beta [+ res] ).  Saves mean/rstd as [n_groups][C] fp32.
  * Replaces bn/relu/"out += residual" at resnet.py:28-29,32,37-38,146-153 and norm/relu at
- * densenet.py:23-24,28-29,73-74,121-122,149,182.  x and out may alias.
- * running_mean/running_var (nullable, together): nn.BatchNorm1d's running statistics, updated once per
- * group IN ORDER (momentum, unbiased variance; SURVEY.md hard part 6) by the last CTA of the launch to finish
- * each channel tile; num_batches_tracked (int64, nullable) += n_groups.  sync_counters: >= ceil(c/32)
- * zero-initialised uint32 tickets (they reset themselves), required when running_mean is given. */
+ * densenet.py:23-24,28-29,73-74,121-122,149,182.  x and out may alias. */
 int dards_gbn_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta,
                   float* save_mean, float* save_rstd, int n_groups, int rows_per_group, int c, int x_stride,
-                  int out_stride, int res_stride, float eps, int relu, float* running_mean, float* running_var,
-                  long long* num_batches_tracked, float momentum, unsigned int* sync_counters, int dtype,
-                  void* stream);
+                  int out_stride, int res_stride, float eps, int relu, int dtype, void* stream);
 
 /* Backward of the above.  g = dout * relu_mask; dx (+)= gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)).
  * relu_mode: 0 none, 1 recompute mask from x (xhat*gamma+beta > 0), 2 mask = (mask_src > 0).
- * dres (optional) receives g (gradient of the residual branch).  Per-group partial sums go to
- * dgamma_part/dbeta_part [n_groups][C]; if dgamma/dbeta (fp32 [C], nullable together) are given, the last
- * CTA to finish each channel tile sums the partials in group order into them (deterministic; needs
- * sync_counters as in dards_gbn_fwd), otherwise the caller reduces them with dards_reduce_rows. */
+ * dres (optional) receives g (gradient of the residual branch).  Per-group partial sums
+ * dgamma_part/dbeta_part [n_groups][C] are reduced with dards_reduce_rows[_batched]. */
 int dards_gbn_bwd(const void* dout, const void* x, const void* mask_src, const float* gamma, const float* beta,
                   const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
-                  float* dgamma_part, float* dbeta_part, float* dgamma, float* dbeta, unsigned int* sync_counters,
-                  int n_groups, int rows_per_group, int c, int dout_stride, int x_stride, int mask_stride,
-                  int dx_stride, int dres_stride, int relu_mode, int dtype, void* stream);
+                  float* dgamma_part, float* dbeta_part, int n_groups, int rows_per_group, int c,
+                  int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode,
+                  int dtype, void* stream);
 
 /* out[c] (+)= sum_r part[r][c]   (fixed order -> deterministic) */
 int dards_reduce_rows(const float* part, float* out, int rows, int c, int accumulate, void* stream);
+/* The same for a whole table of tensors in ONE launch (all BatchNorm dgamma/dbeta of a backward segment).
+ * `descs_dev`: DEVICE array; c % 4 == 0, part/out 16-byte aligned; descriptor j owns ceil(c/64) blocks
+ * starting at first_block_j (first_block_0 = 0); total_blocks = their sum. */
+typedef struct dards_reduce_desc {
+  const float* part;
+  float* out;
+  int rows, c, accumulate, first_block;
+} dards_reduce_desc;
+int dards_reduce_rows_batched(const dards_reduce_desc* descs_dev, int n_descs, int total_blocks, void* stream);
 
 /* nn.BatchNorm1d running statistics, updated once per group IN ORDER (momentum, unbiased variance;
- * SURVEY.md hard part 6); num_batches_tracked (int64) += n_groups. */
+ * SURVEY.md hard part 6); num_batches_tracked (int64) += n_groups.  c % 4 == 0. */
 int dards_bn_running_update(const float* save_mean, const float* save_rstd, float* running_mean,
                             float* running_var, long long* num_batches_tracked, int n_groups,
                             int rows_per_group, int c, float momentum, float eps, void* stream);
+/* The same for every BatchNorm layer of a network in ONE launch (block bookkeeping as above). */
+typedef struct dards_running_desc {
+  const float* save_mean;
+  const float* save_rstd;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked; /* nullable */
+  int n_groups, rows_per_group, c;
+  float momentum;
+  int first_block, reserved;
+} dards_running_desc;
+int dards_bn_running_update_batched(const dards_running_desc* descs_dev, int n_descs, int total_blocks, float eps,
+                                    void* stream);
 
 /* ---- stem: Conv1d(1->C0,k7,s2,p3) + BN + ReLU + Max/AvgPool1d(3,2,1) ---------------- */
 /* resnet.py:143-153 / densenet.py:119-123 fused: x (N,224) fp32 -> out (N,56,C0).  Nothing but the
- * group statistics is saved; the backward recomputes the convolution from x. pool: 0 max, 1 avg.
- * running_mean / running_var / num_batches_tracked / sync_counters (>= C0/16 tickets): as in dards_gbn_fwd. */
+ * group statistics is saved; the backward recomputes the convolution from x. pool: 0 max, 1 avg. */
 int dards_stem_fwd(const float* x, const float* w, const float* gamma, const float* beta, void* out,
                    float* save_mean, float* save_rstd, int n_groups, int group, int c0, int out_stride,
-                   float eps, int pool, float* running_mean, float* running_var, long long* num_batches_tracked,
-                   float momentum, unsigned int* sync_counters, int dtype, void* stream);
-/* dout (N,56,C0) -> per-group partials dw_part [n_groups][C0][7], dgamma_part/dbeta_part [n_groups][C0];
- * if dw (C0*7) / dgamma / dbeta (C0) are given (together), the last CTA per channel slab sums the partials
- * over the groups in order into them (needs sync_counters), otherwise the caller uses dards_reduce_rows. */
+                   float eps, int pool, int dtype, void* stream);
+/* dout (N,56,C0) -> per-group partials dw_part [n_groups][C0][7], dgamma_part/dbeta_part [n_groups][C0]. */
 int dards_stem_bwd(const void* dout, const float* x, const float* w, const float* gamma, const float* beta,
                    const float* save_mean, const float* save_rstd, float* dw_part, float* dgamma_part,
-                   float* dbeta_part, float* dw, float* dgamma, float* dbeta, unsigned int* sync_counters,
-                   int n_groups, int group, int c0, int dout_stride, int pool, int dtype, void* stream);
+                   float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, int dtype,
+                   void* stream);
 
 /* ---- pooling, dropout --------------------------------------------------------------- */
 /* nn.AvgPool1d(2,2) (densenet.py:77): (N,L,C) -> (N,L/2,C) and its backward. */

@@ -249,65 +249,98 @@ def test_bn_running_update_matches_sequential_torch():
     assert int(nbt) == 3
 
 
-@pytest.mark.parametrize("n,c,l,group,dtype", [(120, 64, 14, 20, torch.float32), (5120, 128, 7, 20, torch.bfloat16),
-                                               (60, 96, 28, 20, torch.bfloat16)])
-def test_gbn_fused_running_stats_and_param_grad_reduction(n, c, l, group, dtype):
-    """The last-CTA reductions inside gbn_fwd / gbn_bwd equal the separate kernels (and torch's sequential update)."""
-    g = torch.Generator().manual_seed(21)
-    x = torch.randn(n, c, l, generator=g).to(DEV)
-    bn = torch.nn.BatchNorm1d(c).to(DEV).train()
-    for i in range(0, n, group):
-        bn(x[i:i + group].to(dtype).float())
-    gamma, beta = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
-    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
-    nbt = torch.zeros((), dtype=torch.long, device=DEV)
-    for rep in range(2):  # twice: the tickets must have reset themselves
-        rm.zero_(), rv.fill_(1.0), nbt.zero_()
-        out, mean, rstd = K().gbn_fwd(cl(x).to(dtype), gamma, beta, group * l, True, running=(rm, rv, nbt))
-        assert rel_err(rm, bn.running_mean) < 2e-5
-        assert rel_err(rv, bn.running_var) < 2e-5
-        assert int(nbt) == n // group
-    dy = torch.randn(n, l, c, generator=g).to(DEV).to(dtype)
-    a = K().gbn_bwd(dy, cl(x).to(dtype), gamma, beta, mean, rstd, group * l, 1, fused_reduce=True)
-    b = K().gbn_bwd(dy, cl(x).to(dtype), gamma, beta, mean, rstd, group * l, 1, fused_reduce=False)
-    assert torch.equal(a[0], b[0])
-    assert rel_err(a[1], b[1]) < 1e-6 and rel_err(a[2], b[2]) < 1e-6
-    a2 = K().gbn_bwd(dy, cl(x).to(dtype), gamma, beta, mean, rstd, group * l, 1, fused_reduce=True)
-    assert torch.equal(a[1], a2[1]) and torch.equal(a[2], a2[2])  # deterministic
-
-
-def test_stem_fused_running_stats_and_batched_pack():
-    from deepards_b200 import _lib
+def _desc_table(dt_fields, rows):
     import numpy as np
-    n, c0, group = 100, 64, 20
+    tab = np.zeros(len(rows), dtype=np.dtype(dt_fields))
+    for i, r in enumerate(rows):
+        tab[i] = r
+    return torch.from_numpy(tab.view(np.uint8).copy()).to(DEV)
+
+
+RUNNING_DESC = [("mean", "<u8"), ("rstd", "<u8"), ("rm", "<u8"), ("rv", "<u8"), ("nbt", "<u8"), ("n_groups", "<i4"),
+                ("rows", "<i4"), ("c", "<i4"), ("momentum", "<f4"), ("first_block", "<i4"), ("reserved", "<i4")]
+REDUCE_DESC = [("part", "<u8"), ("out", "<u8"), ("rows", "<i4"), ("c", "<i4"), ("accumulate", "<i4"), ("first_block", "<i4")]
+PACK_DESC = [("w", "<u8"), ("kio", "<u8"), ("koi", "<u8"), ("c_out", "<i4"), ("c_in", "<i4"), ("ktaps", "<i4"),
+             ("first_block", "<i4")]
+
+
+@pytest.mark.parametrize("n,c,l,group,dtype", [(120, 64, 14, 20, torch.float32), (5120, 512, 7, 20, torch.bfloat16),
+                                               (5120, 64, 56, 20, torch.bfloat16), (60, 96, 28, 20, torch.bfloat16),
+                                               (40, 128, 28, 20, torch.bfloat16), (30, 64, 56, 30, torch.bfloat16)])
+def test_gbn_layer_shapes_cached_and_streaming_kernels(n, c, l, group, dtype):
+    """Every tile configuration of the cached kernels (and the streaming fallback for the 30-breath group) against
+    torch, forward and backward, residual + mask variant included."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(n, c, l, generator=g).to(DEV).to(dtype)
+    res = torch.randn(n, c, l, generator=g).to(DEV).to(dtype)
+    gamma = (1 + 0.2 * torch.randn(c, generator=g)).to(DEV).requires_grad_(True)
+    beta = (0.2 * torch.randn(c, generator=g)).to(DEV).requires_grad_(True)
+    dy = torch.randn(n, c, l, generator=g).to(DEV).to(dtype)
+    tol = 1e-5 if dtype == torch.float32 else 1.2e-2
+    xr, rr = x.float().requires_grad_(True), res.float().requires_grad_(True)
+    y_ref = _bn_ref(xr, gamma, beta, group, True, rr)
+    gx, gg, gb, gr = torch.autograd.grad(y_ref, [xr, gamma, beta, rr], dy.float())
+    out, mean, rstd = K().gbn_fwd(cl(x), gamma.detach(), beta.detach(), group * l, True, res=cl(res))
+    assert rel_err(ncl(out).float(), y_ref) < tol
+    # the mask comes from the reference output so that bf16 rounding of `out` cannot flip a decision
+    mask = cl((y_ref > 0).to(dtype))
+    dx, dgamma, dbeta, dres = K().gbn_bwd(cl(dy), cl(x), gamma.detach(), beta.detach(), mean, rstd, group * l, 2,
+                                          mask_src=mask, want_dres=True)
+    assert rel_err(ncl(dx).float(), gx) < tol
+    assert rel_err(dgamma, gg) < tol and rel_err(dbeta, gb) < tol
+    assert rel_err(ncl(dres).float(), gr) < (1e-6 if dtype == torch.float32 else 1e-2)
+    # determinism
+    dx2, dgamma2, dbeta2, _ = K().gbn_bwd(cl(dy), cl(x), gamma.detach(), beta.detach(), mean, rstd, group * l, 2,
+                                          mask_src=mask, want_dres=True)
+    assert torch.equal(dx, dx2) and torch.equal(dgamma, dgamma2) and torch.equal(dbeta, dbeta2)
+
+
+def test_batched_running_update_reduce_rows_and_pack():
+    from deepards_b200 import _lib
+    st = torch.cuda.current_stream().cuda_stream
     g = torch.Generator().manual_seed(22)
-    x = torch.randn(n, 1, 224, generator=g).to(DEV)
-    w = (torch.randn(c0, 1, 7, generator=g) * 0.3).to(DEV)
-    bn = torch.nn.BatchNorm1d(c0).to(DEV).train()
-    for i in range(0, n, group):
-        bn(F.conv1d(x[i:i + group], w, stride=2, padding=3))
-    rm, rv = torch.zeros(c0, device=DEV), torch.ones(c0, device=DEV)
-    nbt = torch.zeros((), dtype=torch.long, device=DEV)
-    K().stem_fwd(x.view(n, 224), w, torch.ones(c0, device=DEV), torch.zeros(c0, device=DEV), group, 0, torch.float32,
-                 running=(rm, rv, nbt))
-    assert rel_err(rm, bn.running_mean) < 2e-5 and rel_err(rv, bn.running_var) < 2e-5 and int(nbt) == n // group
-    # batched weight packing == per-tensor packing
+    # ---- running statistics of several BatchNorm layers in one launch == torch's sequential update ----
+    layers, rows_tab, first = [], [], 0
+    for (n, c, l, group) in [(100, 64, 14, 20), (100, 96, 7, 20), (60, 512, 7, 20)]:
+        x = torch.randn(n, c, l, generator=g).to(DEV)
+        bn = torch.nn.BatchNorm1d(c).to(DEV).train()
+        for i in range(0, n, group):
+            bn(x[i:i + group])
+        _, mean, rstd = K().gbn_fwd(cl(x), torch.ones(c, device=DEV), torch.zeros(c, device=DEV), group * l, False)
+        rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        nbt = torch.zeros((), dtype=torch.long, device=DEV)
+        layers.append((bn, rm, rv, nbt, n // group, mean, rstd))
+        rows_tab.append((mean.data_ptr(), rstd.data_ptr(), rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(), n // group,
+                         group * l, c, 0.1, first, 0))
+        first += (c + 63) // 64
+    tab = _desc_table(RUNNING_DESC, rows_tab)
+    _lib.call("dards_bn_running_update_batched", tab.data_ptr(), len(rows_tab), first, 1e-5, st)
+    for bn, rm, rv, nbt, ng, _, _ in layers:
+        assert rel_err(rm, bn.running_mean) < 2e-5 and rel_err(rv, bn.running_var) < 2e-5 and int(nbt) == ng
+    # ---- batched row reduction ----
+    parts = [torch.randn(r, c, generator=g).to(DEV) for r, c in [(256, 64), (256, 448), (7, 12), (300, 512)]]
+    outs = [torch.full((p.shape[1],), 3.0, device=DEV) for p in parts]
+    rows_tab, first = [], 0
+    for i, (p, o) in enumerate(zip(parts, outs)):
+        rows_tab.append((p.data_ptr(), o.data_ptr(), p.shape[0], p.shape[1], 1 if i == 2 else 0, first))
+        first += (p.shape[1] + 63) // 64
+    tab = _desc_table(REDUCE_DESC, rows_tab)
+    _lib.call("dards_reduce_rows_batched", tab.data_ptr(), len(parts), first, st)
+    for i, (p, o) in enumerate(zip(parts, outs)):
+        assert rel_err(o, p.sum(0) + (3.0 if i == 2 else 0.0)) < 1e-5
+    # ---- batched weight packing == per-tensor packing ----
     shapes = [(64, 64, 3), (128, 64, 1), (512, 256, 3), (32, 128, 3), (40, 24, 5)]
     ws = [torch.randn(s, generator=g).to(DEV) for s in shapes]
-    dt = np.dtype([("w", "<u8"), ("kio", "<u8"), ("koi", "<u8"), ("c_out", "<i4"), ("c_in", "<i4"), ("ktaps", "<i4"),
-                   ("first_block", "<i4")])
-    tab = np.zeros(len(ws), dtype=dt)
-    outs, first = [], 0
-    for i, wt in enumerate(ws):
+    rows_tab, outs, first = [], [], 0
+    for wt in ws:
         co, ci, k = wt.shape
         kio = torch.zeros((k, ci, co), dtype=torch.bfloat16, device=DEV)
         koi = torch.zeros((k, co, ci), dtype=torch.bfloat16, device=DEV)
         outs.append((kio, koi))
-        tab[i] = (wt.data_ptr(), kio.data_ptr(), koi.data_ptr(), co, ci, k, first)
+        rows_tab.append((wt.data_ptr(), kio.data_ptr(), koi.data_ptr(), co, ci, k, first))
         first += ((co + 31) // 32) * ((ci + 31) // 32)
-    tab_dev = torch.from_numpy(tab.view(np.uint8).copy()).to(DEV)
-    _lib.call("dards_pack_conv_weights_batched", tab_dev.data_ptr(), len(ws), first, _lib.BF16,
-              torch.cuda.current_stream().cuda_stream)
+    tab = _desc_table(PACK_DESC, rows_tab)
+    _lib.call("dards_pack_conv_weights_batched", tab.data_ptr(), len(ws), first, _lib.BF16, st)
     for wt, (kio, koi) in zip(ws, outs):
         r_kio, r_koi = K().pack_conv_weight(wt, torch.bfloat16)
         assert torch.equal(kio, r_kio) and torch.equal(koi, r_koi)
