@@ -241,6 +241,9 @@ def run_b200(args):
         "roofline": roof,
         "final_loss": final_loss,
     }
+    if roof:
+        ceil = min(roof["step_ceiling_seq_per_s"].values())
+        line["frac_of_step_ceiling"] = value / world / ceil
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "sequences/s", "cores": cpu_threads, "kind": "port",
                                 "sample": "3 steps of 16 sequences (BASELINE configs[0] shape) of the same training step, "
@@ -278,12 +281,23 @@ def kernel_roofline(trainer, x, t, args, steps=3):
                 d = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
                 d["ms"] += e0.elapsed_time(e1)
                 d["launches"] += 1
+                esz = 2 if args.precision == "bf16" else 4
                 if name == "dards_conv1d_fwd" or name == "dards_conv1d_dgrad":
                     n, l_in, l_out, cin, cout, k = a[4], a[5], a[6], a[7], a[8], a[12]
                     d["flops"] += 2.0 * n * l_out * cin * cout * k
+                    d["bytes"] += esz * n * (l_in * cin + l_out * cout)
                 elif name == "dards_conv1d_wgrad":
                     n, l_in, l_out, cin, cout, k = a[6], a[7], a[8], a[9], a[10], a[13]
                     d["flops"] += 2.0 * n * l_out * cin * cout * k
+                    d["bytes"] += esz * n * (l_in * cin + l_out * cout)
+                elif name == "dards_gbn_fwd":
+                    # algorithmic traffic: x read once, out written once (+ the residual read)
+                    g, rows, c = a[7], a[8], a[9]
+                    d["bytes"] += esz * g * rows * c * (2 + (1 if a[2] else 0))
+                elif name == "dards_gbn_bwd":
+                    # dout and x read once, dx written once (+ mask read, + residual-gradient write, + dx read when accumulating)
+                    g, rows, c = a[12], a[13], a[14]
+                    d["bytes"] += esz * g * rows * c * (3 + (1 if a[2] else 0) + (1 if a[9] else 0) + (1 if a[8] else 0))
         plan.fwd_serial += 1
         plan.bwd_serial = plan.fwd_serial
     total_ms = sum(d["ms"] for d in agg.values())
@@ -297,13 +311,30 @@ def kernel_roofline(trainer, x, t, args, steps=3):
         out.update({"bound": "tensor", "achieved": ach, "peak": P["tf_sustained"], "unit": "TFLOP/s",
                     "frac": ach / P["tf_sustained"], "peak_source": P["src"] + " bf16 sustained (kernel timed inside a long step)"})
     else:
-        out.update({"bound": "hbm", "achieved": None, "peak": P["hbm"], "unit": "GB/s", "frac": None,
-                    "peak_source": P["src"]})
+        ach = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["bytes"] > 0 else None
+        out.update({"bound": "hbm", "achieved": ach, "peak": P["hbm"], "unit": "GB/s",
+                    "frac": ach / P["hbm"] if ach else None, "peak_source": P["src"] + " copy bandwidth"})
+    # measured DRAM traffic per launch of that kernel from the committed `ncu --set full` capture, if there is one
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        out["traffic"] = json.load(open(tpath)).get(args.backbone, {}).get(name)
+    out["per_kernel"] = {}
+    for k, v in agg.items():
+        e = {"ms_per_step": round(v["ms"] / steps, 4), "launches_per_step": v["launches"] / steps}
+        if v["flops"] > 0:
+            e["tflops"] = round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)
+            e["frac_of_tensor_peak"] = round(e["tflops"] / P["tf_sustained"], 3)
+        if v["bytes"] > 0:
+            e["algorithmic_gbs"] = round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1)
+            e["frac_of_hbm_peak"] = round(e["algorithmic_gbs"] / P["hbm"], 3)
+        out["per_kernel"][k] = e
     # whole-step view against the algorithmic ceilings of SURVEY.md section 8d
     conv_ms = sum(v["ms"] for k, v in agg.items() if k.startswith("dards_conv1d")) / steps
     conv_fl = sum(v["flops"] for k, v in agg.items() if k.startswith("dards_conv1d")) / steps
     out["conv_tflops_all"] = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
     out["conv_share_of_step"] = conv_ms / (total_ms / steps)
+    out["step_ceiling_seq_per_s"] = {"tensor": P["tf_sustained"] * 1e12 / FLOP_PER_SEQ[args.backbone],
+                                     "hbm": P["hbm"] * 1e9 / BYTES_PER_SEQ_BF16[args.backbone]}
     return out
 
 
