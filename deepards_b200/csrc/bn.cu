@@ -89,47 +89,66 @@ __device__ __forceinline__ void rowlane_reduce(float (&v)[NV], float* red /* [TH
   for (int j = 0; j < NV; ++j) v[j] = red[NW * W + cq * NV + j];
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, L2-only caching: the data is read once)
+__device__ __forceinline__ void cp_async16(const void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The cached kernels are PERSISTENT: gridDim.x CTAs walk the (group, channel tile) list round-robin.  A tile is
+// brought in with cp.async (no registers, the whole tile in flight at once); while the last sweep of tile i reads
+// row k out of the cache and stores its result, it refills slot k with row k of tile i+1 -- so the loads of the next
+// tile overlap the stores of the current one and an SM always has a full tile of requests outstanding.
 template <typename T, int VPR, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     gbn_fwd_cached_kernel(const T* x, T* out, const T* res, const float* __restrict__ gamma, const float* __restrict__ beta,
-                          float* __restrict__ save_mean, float* __restrict__ save_rstd, int rows, int c, int x_stride,
-                          int out_stride, int res_stride, float eps, int relu) {
+                          float* __restrict__ save_mean, float* __restrict__ save_rstd, int n_groups, int rows, int c,
+                          int x_stride, int out_stride, int res_stride, float eps, int relu) {
   constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V, U = BN_UNROLL;
   extern __shared__ uint4 cache[];  // [K][THREADS]
   __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
-  const int g = blockIdx.y;
   const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
-  const int c0 = blockIdx.x * CT + cq * V;
-  const bool active = c0 < c;
-  const size_t row_base = (size_t)g * rows;
   const float inv_n = 1.f / (float)rows;
   const int K = (rows + LANES - 1) / LANES;
-  const T* xp = x + row_base * x_stride + c0;
+  const int n_ct = (c + CT - 1) / CT;
+  const int n_tiles = n_ct * n_groups;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-
-  // ---- sweep 1 (global): park the tile; shifted sums  sum(x - s), sum((x - s)^2)  with s = the group's first row.
-  // One pass with fp32-faithful variance: the shift is a sample of the data, so |mean - s| ~ std and the
-  // subtraction  E[d^2] - E[d]^2  cancels at most a digit (a plain sum of squares would lose |mean|^2/var). ----
-  float acc[2 * V], shift[V];
-#pragma unroll
-  for (int j = 0; j < 2 * V; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < V; ++j) shift[j] = 0.f;
-  if (active) {
-    Vec<T>::unpack(ld16(xp), shift);
-    for (int k0 = 0; k0 < K; k0 += U) {
-      uint4 raw[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = rl + (k0 + u) * LANES;
-        raw[u] = r < rows ? ld16(xp + (size_t)r * x_stride) : zero4;
+  // first element of this thread's channel vector in the tile, or nullptr past the last channel
+  auto tile_x = [&](int tile) -> const T* {
+    const int c0 = (tile % n_ct) * CT + cq * V;
+    return c0 < c ? x + (size_t)(tile / n_ct) * rows * x_stride + c0 : nullptr;
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles) {
+    const T* xp = tile_x(tile);
+    if (xp)
+      for (int k = 0; k < K; ++k) {
+        const int r = rl + k * LANES;
+        if (r < rows) cp_async16(&cache[k * THREADS + threadIdx.x], xp + (size_t)r * x_stride);
       }
+  }
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int g = tile / n_ct, c0 = (tile % n_ct) * CT + cq * V;
+    const bool active = c0 < c;
+    const size_t row_base = (size_t)g * rows;
+    const T* xnext = tile + gridDim.x < n_tiles ? tile_x(tile + gridDim.x) : nullptr;
+    cp_async_wait_all();
+    __syncthreads();  // row 0 (the shift) is read from another thread's slot
+    // ---- sweep 1 (shared): shifted sums  sum(x - s), sum((x - s)^2)  with s = the group's first row.  One pass
+    // with fp32-faithful variance: the shift is a sample of the data, so |mean - s| ~ std and the subtraction
+    // E[d^2] - E[d]^2  cancels at most a digit (a plain sum of squares would lose |mean|^2/var). ----
+    float acc[2 * V], shift[V];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (rl + (k0 + u) * LANES < rows) {
-          cache[(k0 + u) * THREADS + threadIdx.x] = raw[u];
+    for (int j = 0; j < 2 * V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) shift[j] = 0.f;
+    if (active) {
+      Vec<T>::unpack(cache[cq], shift);  // row 0 lives in slot 0 of the thread with row lane 0
+      for (int k = 0; k < K; ++k) {
+        if (rl + k * LANES < rows) {
           float v[V];
-          Vec<T>::unpack(raw[u], v);
+          Vec<T>::unpack(cache[k * THREADS + threadIdx.x], v);
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const float d = v[j] - shift[j];
@@ -139,122 +158,138 @@ __global__ void __launch_bounds__(THREADS)
         }
       }
     }
-  }
-  rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
-  if (!active) return;
-  float sc[V], sh[V];
+    rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
+    float sc[V], sh[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const float md = acc[j] * inv_n;  // mean - shift
-    const float var = fmaxf(fmaf(-md, md, acc[V + j] * inv_n), 0.f) + eps;
-    const float mean = shift[j] + md;
-    float rstd = rsqrtf(var);
-    rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);  // one Newton step: the reference divides by sqrt()
-    sc[j] = rstd * gamma[c0 + j];
-    sh[j] = beta[c0 + j] - mean * sc[j];
-    if (rl == 0) {
-      save_mean[(size_t)g * c + c0 + j] = mean;
-      save_rstd[(size_t)g * c + c0 + j] = rstd;
-    }
-  }
-  // ---- sweep 2 (shared -> global): normalise (+residual) (+ReLU) ----
-  T* op = out + row_base * out_stride + c0;
-  const T* rp = res ? res + row_base * res_stride + c0 : nullptr;
-  for (int k0 = 0; k0 < K; k0 += U) {
-    uint4 rres[U];
+    for (int j = 0; j < V; ++j) sc[j] = sh[j] = 0.f;
+    if (active) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = rl + (k0 + u) * LANES;
-      rres[u] = (rp && r < rows) ? ld16(rp + (size_t)r * res_stride) : zero4;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = rl + (k0 + u) * LANES;
-      if (r < rows) {
-        float v[V];
-        Vec<T>::unpack(cache[(k0 + u) * THREADS + threadIdx.x], v);
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-        if (rp) {
-          float e[V];
-          Vec<T>::unpack(rres[u], e);
-#pragma unroll
-          for (int j = 0; j < V; ++j) v[j] += e[j];
+      for (int j = 0; j < V; ++j) {
+        const float md = acc[j] * inv_n;  // mean - shift
+        const float var = fmaxf(fmaf(-md, md, acc[V + j] * inv_n), 0.f) + eps;
+        const float mean = shift[j] + md;
+        float rstd = rsqrtf(var);
+        rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);  // one Newton step: the reference divides by sqrt()
+        sc[j] = rstd * gamma[c0 + j];
+        sh[j] = beta[c0 + j] - mean * sc[j];
+        if (rl == 0) {
+          save_mean[(size_t)g * c + c0 + j] = mean;
+          save_rstd[(size_t)g * c + c0 + j] = rstd;
         }
-        if (relu) {
-#pragma unroll
-          for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        st16(op + (size_t)r * out_stride, Vec<T>::pack(v));
       }
     }
-  }
-}
-
-template <typename T, int VPR, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-    gbn_bwd_cached_kernel(const T* dout, const T* x, const T* mask_src, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, const float* __restrict__ save_mean,
-                          const float* __restrict__ save_rstd, T* dx, int accumulate_dx, T* dres,
-                          float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int rows, int c, int dout_stride,
-                          int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode) {
-  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V, U = BN_UNROLL;
-  extern __shared__ uint4 cache[];  // [2][K][THREADS]: masked gradient, then x
-  __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
-  const int g = blockIdx.y;
-  const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
-  const int c0 = blockIdx.x * CT + cq * V;
-  const bool active = c0 < c;
-  const size_t row_base = (size_t)g * rows;
-  const float inv_n = 1.f / (float)rows;
-  const int K = (rows + LANES - 1) / LANES;
-  uint4* cache_g = cache;
-  uint4* cache_x = cache + (size_t)K * THREADS;
-  const T* gp = dout + row_base * dout_stride + c0;
-  const T* xp = x + row_base * x_stride + c0;
-  const T* mp = relu_mode == 2 ? mask_src + row_base * mask_stride + c0 : nullptr;
-  T* drp = dres ? dres + row_base * dres_stride + c0 : nullptr;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-
-  float mean[V], rstd[V], sc[V], sh[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    mean[j] = active ? save_mean[(size_t)g * c + c0 + j] : 0.f;
-    rstd[j] = active ? save_rstd[(size_t)g * c + c0 + j] : 0.f;
-    const float gm = active ? gamma[c0 + j] : 0.f, bt = active ? beta[c0 + j] : 0.f;
-    sc[j] = rstd[j] * gm;          // same arithmetic as the forward: y = fmaf(x, sc, sh)
-    sh[j] = bt - mean[j] * sc[j];
-  }
-
-  // ---- sweep 1 (global): mask the gradient, park (g, x), accumulate sum g and sum g*xhat ----
-  float acc[2 * V];
-#pragma unroll
-  for (int j = 0; j < 2 * V; ++j) acc[j] = 0.f;
-  if (active) {
+    // ---- sweep 2 (shared -> global): normalise (+residual) (+ReLU); refill the cache with the next tile ----
+    T* op = out + row_base * out_stride + c0;
+    const T* rp = (res && active) ? res + row_base * res_stride + c0 : nullptr;
     for (int k0 = 0; k0 < K; k0 += U) {
-      uint4 rg[U], rx[U], rk[U];
+      uint4 rres[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int r = rl + (k0 + u) * LANES;
-        const bool ok = r < rows;
-        rg[u] = ok ? ld16(gp + (size_t)r * dout_stride) : zero4;
-        rx[u] = ok ? ld16(xp + (size_t)r * x_stride) : zero4;
-        rk[u] = (ok && mp) ? ld16(mp + (size_t)r * mask_stride) : zero4;
+        rres[u] = (rp && r < rows) ? ld16(rp + (size_t)r * res_stride) : zero4;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int r = rl + (k0 + u) * LANES;
         if (r < rows) {
+          uint4* slot = &cache[(k0 + u) * THREADS + threadIdx.x];
+          const uint4 raw = *slot;
+          if (xnext) cp_async16(slot, xnext + (size_t)r * x_stride);
+          if (active) {
+            float v[V];
+            Vec<T>::unpack(raw, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            if (rp) {
+              float e[V];
+              Vec<T>::unpack(rres[u], e);
+#pragma unroll
+              for (int j = 0; j < V; ++j) v[j] += e[j];
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            st16(op + (size_t)r * out_stride, Vec<T>::pack(v));
+          }
+        }
+      }
+    }
+  }
+}
+
+// NT = number of cached tensors: 2 (gradient, x) or 3 (+ the ReLU mask source of relu_mode 2)
+template <typename T, int VPR, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    gbn_bwd_cached_kernel(const T* dout, const T* x, const T* mask_src, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ save_mean,
+                          const float* __restrict__ save_rstd, T* dx, int accumulate_dx, T* dres,
+                          float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int n_groups, int rows, int c,
+                          int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode) {
+  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V, U = BN_UNROLL;
+  extern __shared__ uint4 cache[];  // [NT][K][THREADS]: gradient (masked in place by sweep 1), x, [mask source]
+  __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
+  const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
+  const float inv_n = 1.f / (float)rows;
+  const int K = (rows + LANES - 1) / LANES;
+  const int n_ct = (c + CT - 1) / CT;
+  const int n_tiles = n_ct * n_groups;
+  uint4* cache_g = cache;
+  uint4* cache_x = cache + (size_t)K * THREADS;
+  uint4* cache_m = cache + (size_t)2 * K * THREADS;
+  const bool use_mask = relu_mode == 2;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  // element offset of this thread's channel vector in row 0 of the tile (in units of rows*stride + c0), or -1
+  auto tile_c0 = [&](int tile) { return (tile % n_ct) * CT + cq * V; };
+  auto issue_row = [&](int tile, int k, int r) {
+    const size_t row = (size_t)(tile / n_ct) * rows + r;
+    const int c0 = tile_c0(tile);
+    cp_async16(&cache_g[k * THREADS + threadIdx.x], dout + row * dout_stride + c0);
+    cp_async16(&cache_x[k * THREADS + threadIdx.x], x + row * x_stride + c0);
+    if (use_mask) cp_async16(&cache_m[k * THREADS + threadIdx.x], mask_src + row * mask_stride + c0);
+  };
+  int tile = blockIdx.x;
+  if (tile < n_tiles && tile_c0(tile) < c)
+    for (int k = 0; k < K; ++k) {
+      const int r = rl + k * LANES;
+      if (r < rows) issue_row(tile, k, r);
+    }
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int g = tile / n_ct, c0 = tile_c0(tile);
+    const bool active = c0 < c;
+    const size_t row_base = (size_t)g * rows;
+    const int next = tile + gridDim.x;
+    const bool refill = next < n_tiles && tile_c0(next) < c;
+    float mean[V], rstd[V], sc[V], sh[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      mean[j] = active ? save_mean[(size_t)g * c + c0 + j] : 0.f;
+      rstd[j] = active ? save_rstd[(size_t)g * c + c0 + j] : 0.f;
+      const float gm = active ? gamma[c0 + j] : 0.f, bt = active ? beta[c0 + j] : 0.f;
+      sc[j] = rstd[j] * gm;          // same arithmetic as the forward: y = fmaf(x, sc, sh)
+      sh[j] = bt - mean[j] * sc[j];
+    }
+    cp_async_wait_all();  // every thread only reads the slots it filled itself: no barrier needed
+
+    // ---- sweep 1 (shared): mask the gradient in place, accumulate sum g and sum g*(x - mean) ----
+    float acc[2 * V];
+#pragma unroll
+    for (int j = 0; j < 2 * V; ++j) acc[j] = 0.f;
+    T* drp = (dres && active) ? dres + row_base * dres_stride + c0 : nullptr;
+    if (active) {
+      for (int k = 0; k < K; ++k) {
+        const int r = rl + k * LANES;
+        if (r < rows) {
           float gv[V], xv[V];
-          Vec<T>::unpack(rg[u], gv);
-          Vec<T>::unpack(rx[u], xv);
+          Vec<T>::unpack(cache_g[k * THREADS + threadIdx.x], gv);
+          Vec<T>::unpack(cache_x[k * THREADS + threadIdx.x], xv);
           if (relu_mode == 1) {
 #pragma unroll
             for (int j = 0; j < V; ++j)
               if (!(fmaf(xv[j], sc[j], sh[j]) > 0.f)) gv[j] = 0.f;
           } else if (relu_mode == 2) {
             float m[V];
-            Vec<T>::unpack(rk[u], m);
+            Vec<T>::unpack(cache_m[k * THREADS + threadIdx.x], m);
 #pragma unroll
             for (int j = 0; j < V; ++j)
               if (!(m[j] > 0.f)) gv[j] = 0.f;
@@ -264,58 +299,68 @@ __global__ void __launch_bounds__(THREADS)
             acc[j] += gv[j];
             acc[V + j] = fmaf(gv[j], xv[j] - mean[j], acc[V + j]);  // x rstd after the reduction
           }
-          const uint4 pg = Vec<T>::pack(gv);  // exact: masking keeps or zeroes a value that already is a T
-          cache_g[(k0 + u) * THREADS + threadIdx.x] = pg;
-          cache_x[(k0 + u) * THREADS + threadIdx.x] = rx[u];
-          if (drp) st16(drp + (size_t)r * dres_stride, pg);
+          if (relu_mode != 0) {
+            const uint4 pg = Vec<T>::pack(gv);  // exact: masking keeps or zeroes a value that already is a T
+            cache_g[k * THREADS + threadIdx.x] = pg;
+            if (drp) st16(drp + (size_t)r * dres_stride, pg);
+          } else if (drp) {
+            st16(drp + (size_t)r * dres_stride, cache_g[k * THREADS + threadIdx.x]);
+          }
         }
       }
     }
-  }
-  rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
-  if (!active) return;
+    rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
+    float kb[V], kc[V];
 #pragma unroll
-  for (int j = 0; j < V; ++j) acc[V + j] *= rstd[j];
-  if (rl == 0) {
+    for (int j = 0; j < V; ++j) kb[j] = kc[j] = 0.f;
+    if (active) {
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      if (dbeta_part) dbeta_part[(size_t)g * c + c0 + j] = acc[j];
-      if (dgamma_part) dgamma_part[(size_t)g * c + c0 + j] = acc[V + j];
-    }
-  }
-  // dx = sc*(g - m1 - xhat*m2) = sc*g + kb*x + kc
-  float kb[V], kc[V];
+      for (int j = 0; j < V; ++j) acc[V + j] *= rstd[j];
+      if (rl == 0) {
 #pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const float m1 = acc[j] * inv_n, m2 = acc[V + j] * inv_n;
-    kb[j] = -sc[j] * m2 * rstd[j];
-    kc[j] = -sc[j] * m1 - kb[j] * mean[j];
-  }
-  // ---- sweep 2 (shared -> global) ----
-  T* dxp = dx + row_base * dx_stride + c0;
-  for (int k0 = 0; k0 < K; k0 += U) {
-    uint4 ro[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = rl + (k0 + u) * LANES;
-      ro[u] = (accumulate_dx && r < rows) ? ld16(dxp + (size_t)r * dx_stride) : zero4;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = rl + (k0 + u) * LANES;
-      if (r < rows) {
-        float gv[V], xv[V], o[V];
-        Vec<T>::unpack(cache_g[(k0 + u) * THREADS + threadIdx.x], gv);
-        Vec<T>::unpack(cache_x[(k0 + u) * THREADS + threadIdx.x], xv);
-#pragma unroll
-        for (int j = 0; j < V; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(kb[j], xv[j], kc[j]));
-        if (accumulate_dx) {
-          float e[V];
-          Vec<T>::unpack(ro[u], e);
-#pragma unroll
-          for (int j = 0; j < V; ++j) o[j] += e[j];
+        for (int j = 0; j < V; ++j) {
+          if (dbeta_part) dbeta_part[(size_t)g * c + c0 + j] = acc[j];
+          if (dgamma_part) dgamma_part[(size_t)g * c + c0 + j] = acc[V + j];
         }
-        st16(dxp + (size_t)r * dx_stride, Vec<T>::pack(o));
+      }
+      // dx = sc*(g - m1 - xhat*m2) = sc*g + kb*x + kc
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float m1 = acc[j] * inv_n, m2 = acc[V + j] * inv_n;
+        kb[j] = -sc[j] * m2 * rstd[j];
+        kc[j] = -sc[j] * m1 - kb[j] * mean[j];
+      }
+    }
+    // ---- sweep 2 (shared -> global): dx; refill the cache with the next tile ----
+    T* dxp = dx + row_base * dx_stride + c0;
+    for (int k0 = 0; k0 < K; k0 += U) {
+      uint4 ro[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rl + (k0 + u) * LANES;
+        ro[u] = (accumulate_dx && active && r < rows) ? ld16(dxp + (size_t)r * dx_stride) : zero4;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u, r = rl + k * LANES;
+        if (r < rows) {
+          const uint4 rg = cache_g[k * THREADS + threadIdx.x], rx = cache_x[k * THREADS + threadIdx.x];
+          if (refill) issue_row(next, k, r);
+          if (active) {
+            float gv[V], xv[V], o[V];
+            Vec<T>::unpack(rg, gv);
+            Vec<T>::unpack(rx, xv);
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(kb[j], xv[j], kc[j]));
+            if (accumulate_dx) {
+              float e[V];
+              Vec<T>::unpack(ro[u], e);
+#pragma unroll
+              for (int j = 0; j < V; ++j) o[j] += e[j];
+            }
+            st16(dxp + (size_t)r * dx_stride, Vec<T>::pack(o));
+          }
+        }
       }
     }
   }
@@ -648,11 +693,21 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
 // ---- host launchers ------------------------------------------------------------------------------
 static int vec_of(int dtype) { return dtype == DARDS_BF16 ? 8 : 4; }
 
+static int bn_sm_count() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  return n;
+}
+
 // cached-kernel configurations: (threads, vectors per row) in order of preference for a given row count
 struct BnCfg { int threads, vpr; };
 static const BnCfg kBnCfgs[] = {{256, 16}, {256, 8}, {256, 4}, {512, 4}};
 constexpr int BN_MAX_K = 9;                 // rows per thread (bounds the cache: 9 * threads * 16 B per tensor)
-constexpr int BN_CACHE_LIMIT = 200 * 1024;  // dynamic shared memory we are willing to ask for
+constexpr int BN_CACHE_LIMIT = 222 * 1024;  // dynamic shared memory we are willing to ask for (3 x 72 KB tiles fit)
 
 // picks a configuration whose tile holds the whole group; -1 -> use the streaming kernels
 static int bn_pick_cfg(int rows, int c, int v, int tensors) {
@@ -681,6 +736,16 @@ static int bn_smem_optin(K kernel, size_t smem, size_t* granted) {
   return DARDS_OK;
 }
 
+// persistent grid: as many CTAs per SM as the tile's shared memory allows (at most 4; 2048 threads per SM)
+static int bn_persistent_grid(size_t smem_dyn, size_t smem_static, int threads, int n_tiles) {
+  int per_sm = (int)((227 * 1024) / (smem_dyn + smem_static + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm * threads > 2048) per_sm = 2048 / threads;
+  if (per_sm < 1) per_sm = 1;
+  int grid = per_sm * bn_sm_count();
+  return grid < n_tiles ? grid : n_tiles;
+}
+
 template <typename T, int VPR, int THREADS>
 static int run_fwd_cached(const void* x, void* out, const void* res, const float* gamma, const float* beta,
                           float* save_mean, float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride,
@@ -689,10 +754,11 @@ static int run_fwd_cached(const void* x, void* out, const void* res, const float
   const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16;
   int rc = bn_smem_optin(gbn_fwd_cached_kernel<T, VPR, THREADS>, smem, &granted);
   if (rc) return rc;
-  dim3 grid(ceil_div(c, VPR * Vec<T>::N), n_groups);
+  const int n_tiles = ceil_div(c, VPR * Vec<T>::N) * n_groups;
+  const int grid = bn_persistent_grid(smem, (THREADS / 32 + 1) * VPR * 2 * Vec<T>::N * 4, THREADS, n_tiles);
   gbn_fwd_cached_kernel<T, VPR, THREADS><<<grid, THREADS, smem, st>>>(
-      static_cast<const T*>(x), static_cast<T*>(out), static_cast<const T*>(res), gamma, beta, save_mean, save_rstd, rows, c,
-      x_stride, out_stride, res_stride, eps, relu);
+      static_cast<const T*>(x), static_cast<T*>(out), static_cast<const T*>(res), gamma, beta, save_mean, save_rstd,
+      n_groups, rows, c, x_stride, out_stride, res_stride, eps, relu);
   return DARDS_OK;
 }
 
@@ -702,14 +768,15 @@ static int run_bwd_cached(const void* dout, const void* x, const void* mask_src,
                           float* dgamma_part, float* dbeta_part, int n_groups, int rows, int c, int dout_stride,
                           int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode, cudaStream_t st) {
   static size_t granted = 24 * 1024;
-  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16 * 2;
+  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16 * (relu_mode == 2 ? 3 : 2);
   int rc = bn_smem_optin(gbn_bwd_cached_kernel<T, VPR, THREADS>, smem, &granted);
   if (rc) return rc;
-  dim3 grid(ceil_div(c, VPR * Vec<T>::N), n_groups);
+  const int n_tiles = ceil_div(c, VPR * Vec<T>::N) * n_groups;
+  const int grid = bn_persistent_grid(smem, (THREADS / 32 + 1) * VPR * 2 * Vec<T>::N * 4, THREADS, n_tiles);
   gbn_bwd_cached_kernel<T, VPR, THREADS><<<grid, THREADS, smem, st>>>(
       static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,
-      save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, rows, c, dout_stride,
-      x_stride, mask_stride, dx_stride, dres_stride, relu_mode);
+      save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, n_groups, rows, c,
+      dout_stride, x_stride, mask_stride, dx_stride, dres_stride, relu_mode);
   return DARDS_OK;
 }
 
@@ -761,7 +828,7 @@ int launch_gbn_bwd(const void* dout, const void* x, const void* mask_src, const 
   DARDS_CHECK_ARG(!dres || dres_stride % v == 0, "gbn_bwd: dres stride");
   if (n_groups == 0) return DARDS_OK;
   DARDS_CHECK_ARG(n_groups <= 65535, "gbn_bwd: too many groups (%d)", n_groups);
-  const int cfg = bn_pick_cfg(rows, c, v, 2);
+  const int cfg = bn_pick_cfg(rows, c, v, relu_mode == 2 ? 3 : 2);
   if (cfg >= 0) {
     int rc = DARDS_OK;
     DARDS_DISPATCH_DTYPE(dtype, {
