@@ -24,12 +24,12 @@
 
 namespace dards {
 
-int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1;
+int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1;
 
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
-constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_BLOCK_M = 128;          // output channels per tile (TMEM lanes)
 constexpr int TC_BLOCK_K = 64;           // reduction channels per stage = one 128-byte swizzle row
 constexpr int TC_MAX_N = 256;            // positions per tile (TMEM columns per accumulator)
@@ -37,7 +37,11 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;   // 16 KB
 constexpr int TC_B_BYTES = TC_MAX_N * TC_BLOCK_K * 2;     // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_STAGING_BYTES = TC_MAX_N * TC_BLOCK_M * 2;  // 64 KB: [pos][co] bf16
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// shared memory: `stages` operand stages, then the staging tile (whole tile, or half of it when the epilogue stores
+// the tile in two halves to make room for a 4th stage), alignment slack, barriers
+static int tc_smem_bytes(int stages, int halves) {
+  return stages * TC_STAGE_BYTES + TC_STAGING_BYTES / halves + 1024 + 256;
+}
 constexpr int TC_MAX_TAPS = 8;
 
 struct TcConvParams {
@@ -55,8 +59,11 @@ struct TcConvParams {
   int accumulate;             // destination += result
   int tma_epilogue;           // 1: staging tile + TMA store; 0: direct global stores (debug fallback)
   int n_pos_tiles, n_co_tiles;
+  int stages;                 // operand ring depth (3 or 4)
+  int halves;                 // 1: one store per tile; 2: two stores of nb/2 breaths through a half-size staging tile
 };
 
+template <int HALVES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_conv_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                    const __grid_constant__ CUtensorMap tm_o, __nv_bfloat16* __restrict__ out, const TcConvParams p,
@@ -64,14 +71,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t staging = smem_base + TC_STAGES * TC_STAGE_BYTES;
-  const uint32_t bar_base = staging + TC_STAGING_BYTES;
+  const int n_stages = p.stages;
+  const uint32_t staging = smem_base + n_stages * TC_STAGE_BYTES;
+  const uint32_t bar_base = staging + TC_STAGING_BYTES / HALVES;
   // barrier layout (8 bytes each): full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * TC_STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * TC_MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -84,7 +92,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_o);
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_arrive_expect_tx(full_bar(stage), stage_tx);
             tma_load_3d(sa, &tm_w, full_bar(stage), kc * TC_BLOCK_K, co0, p.w_tap[ti]);
             tma_load_4d(sb, &tm_x, full_bar(stage), kc * TC_BLOCK_K, p.in_par[ti], p.in_start[ti], n0);
-            if (++stage == TC_STAGES) {
+            if (++stage == n_stages) {
               stage = 0;
               phase ^= 1u;
             }
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs are done
-          if (++stage == TC_STAGES) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -183,27 +191,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * TC_MAX_N;
       if (p.tma_epilogue) {
-        // the previous tile's TMA store must have finished reading the staging tile
-        if (leader) tma_store_wait_read();
-        named_bar_sync(1, TC_EPI_THREADS);
         __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_gen + (staging - smem_base));
-        for (int ch = chunk_lo; ch < chunk_hi; ++ch) {
-          uint32_t v[16];
-          tmem_ld16(t_row + (uint32_t)(ch << 4), v);
-          tmem_ld_wait();
+        constexpr int n_halves = HALVES;
+        const int cols_h = n_tile / n_halves;  // columns per store: nb/halves whole breaths
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            stg[((ch << 4) + j) * TC_BLOCK_M + cl] = __float2bfloat16_rn(__uint_as_float(v[j]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));  // TMEM buffer may be overwritten by the next-but-one tile
-        fence_proxy_async();
-        named_bar_sync(1, TC_EPI_THREADS);
-        if (leader) {
-          if (p.accumulate) tma_reduce_add_4d(&tm_o, staging, co0, p.out_par, 0, n0);
-          else tma_store_4d(&tm_o, staging, co0, p.out_par, 0, n0);
-          tma_store_commit();
+        for (int h = 0; h < n_halves; ++h) {
+          // the previous TMA store must have finished reading the staging tile
+          if (leader) tma_store_wait_read();
+          named_bar_sync(1, TC_EPI_THREADS);
+          const int col_lo = h * cols_h, col_hi = col_lo + cols_h;
+          for (int ch = (col_lo >> 4) + half; (ch << 4) < col_hi; ch += 2) {
+            uint32_t v[16];
+            tmem_ld16(t_row + (uint32_t)(ch << 4), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = (ch << 4) + j;
+              if (HALVES == 1 || (col >= col_lo && col < col_hi))  // a 16-column chunk may straddle the two halves
+                stg[(col - col_lo) * TC_BLOCK_M + cl] = __float2bfloat16_rn(__uint_as_float(v[j]));
+            }
+          }
+          if (h == n_halves - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));  // TMEM buffer may be overwritten by the next-but-one tile
+          }
+          fence_proxy_async();
+          named_bar_sync(1, TC_EPI_THREADS);
+          if (leader) {
+            const int nh = n0 + h * (p.nb / n_halves);
+            if (p.accumulate) tma_reduce_add_4d(&tm_o, staging, co0, p.out_par, 0, nh);
+            else tma_store_4d(&tm_o, staging, co0, p.out_par, 0, nh);
+            tma_store_commit();
+          }
         }
       } else {
         const int co = co0 + cl;
@@ -237,6 +257,231 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
     if (p.tma_epilogue && leader) tma_store_wait_all();  // global writes complete before the CTA exits
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ===================================================================================================
+// v3: 3-tap, stride-1, pad-1 convolutions (16 of ResNet-18's 20 convs, forward and dgrad) with ONE activation load
+// for all three taps.
+//
+// The activation tile is staged WITH its halo: the TMA box is (64 ch, L+2 positions starting at -1, NB breaths), so
+// breath b occupies staged rows b(L+2) .. b(L+2)+L+1 = positions -1 .. L, the out-of-range rows zero-filled by the
+// TMA unit (= the conv padding).  Output column j = b(L+2) + q then needs staged row j + t for tap t: the SAME tile
+// read through a shared-memory descriptor whose start is advanced by t rows (t * 128 B; the 128-byte swizzle is a
+// function of the absolute shared-memory address, so a row-shifted start needs no other change).  Columns with
+// q >= L straddle two breaths; they are computed and dropped (2 of every L+2 columns).
+// Versus one load per tap this cuts the shared-memory fill per MMA from (A+B) to (A + B/3): an SS-mode tcgen05.mma
+// already reads (M+N)*32 B per K=16 step, and TMA writes + MMA reads share the SM's 128 B/clk.
+// Two rings: activation tiles (one per 64-channel chunk, 3 stages) and weight tiles (one per chunk and tap, 4 stages).
+// The epilogue writes the tile in two halves of NB/2 breaths, each through its own 32 KB staging buffer, so the
+// TMEM -> shared transposition of one half overlaps the TMA store of the other.
+constexpr int C3_B_STAGES = 2;
+constexpr int C3_A_STAGES = 4;
+constexpr int C3_EPI_WARPS = 16;  // 4 per TMEM lane quarter: the epilogue is 2-byte shared-memory stores, it needs warps
+constexpr int C3_EPI_THREADS = C3_EPI_WARPS * 32;
+constexpr int C3_THREADS = 64 + C3_EPI_THREADS;
+constexpr int C3_MAX_ROWS = 258;                                       // staged rows read by the MMAs (N <= 256, + 2)
+constexpr int C3_B_BYTES = ((C3_MAX_ROWS * 128 + 1023) / 1024) * 1024;  // 33 KB
+constexpr int C3_STAGING_BYTES = 128 * 128 * 2;                        // <= 128 compact rows x 128 channels, bf16
+constexpr int C3_SMEM_BYTES = C3_B_STAGES * C3_B_BYTES + C3_A_STAGES * TC_A_BYTES + 2 * C3_STAGING_BYTES + 1024 + 256;
+
+struct TcConv3Params {
+  int w_tap[3];   // weight tap used with a row shift of 0, 1, 2
+  int k_chunks;   // ceil(reduction channels / 64)
+  int nb, l;      // breaths per tile (even), positions per breath
+  int n_cols;     // MMA N: nb*(l+2) - 2 rounded up to 16
+  int n_pos_tiles, n_co_tiles;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(C3_THREADS, 1)
+    tc_conv3_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                    const __grid_constant__ CUtensorMap tm_o, const TcConv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base;
+  const uint32_t a_base = b_base + C3_B_STAGES * C3_B_BYTES;
+  const uint32_t staging = a_base + C3_A_STAGES * TC_A_BYTES;
+  const uint32_t bar_base = staging + 2 * C3_STAGING_BYTES;
+  auto fullb = [&](int s) { return bar_base + 8u * s; };
+  auto emptyb = [&](int s) { return bar_base + 8u * (C3_B_STAGES + s); };
+  auto fulla = [&](int s) { return bar_base + 8u * (2 * C3_B_STAGES + s); };
+  auto emptya = [&](int s) { return bar_base + 8u * (2 * C3_B_STAGES + C3_A_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * C3_B_STAGES + 2 * C3_A_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * C3_B_STAGES + 2 * C3_A_STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C3_B_STAGES + 2 * C3_A_STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.n_pos_tiles * p.n_co_tiles;
+  const int lp = p.l + 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_o);
+    for (int s = 0; s < C3_B_STAGES; ++s) {
+      mbar_init(fullb(s), 1);
+      mbar_init(emptyb(s), 1);
+    }
+    for (int s = 0; s < C3_A_STAGES; ++s) {
+      mbar_init(fulla(s), 1);
+      mbar_init(emptya(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), C3_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      const uint32_t b_tx = (uint32_t)(p.nb * lp) * 128u;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int co0 = (tile % p.n_co_tiles) * TC_BLOCK_M, n0 = (tile / p.n_co_tiles) * p.nb;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(emptyb(sb), phb ^ 1u);
+          mbar_arrive_expect_tx(fullb(sb), b_tx);
+          tma_load_4d(b_base + sb * C3_B_BYTES, &tm_x, fullb(sb), kc * TC_BLOCK_K, 0, -1, n0);
+          if (++sb == C3_B_STAGES) {
+            sb = 0;
+            phb ^= 1u;
+          }
+          for (int t = 0; t < 3; ++t) {
+            mbar_wait(emptya(sa), pha ^ 1u);
+            mbar_arrive_expect_tx(fulla(sa), TC_A_BYTES);
+            tma_load_3d(a_base + sa * TC_A_BYTES, &tm_w, fulla(sa), kc * TC_BLOCK_K, co0, p.w_tap[t]);
+            if (++sa == C3_A_STAGES) {
+              sa = 0;
+              pha ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_cols >> 3) << 17) |
+                             ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+      const uint64_t tmpl = make_sw128_desc(0, 1, 1024 >> 4, 1, 0);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(tempty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_MAX_N;
+        uint32_t acc = 0u;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(fullb(sb), phb);
+          const uint64_t b_desc = tmpl + (uint64_t)((b_base + sb * C3_B_BYTES) >> 4);
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            mbar_wait(fulla(sa), pha);
+            tc_fence_after();
+            const uint64_t a_desc = tmpl + (uint64_t)((a_base + sa * TC_A_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+              // tap t: start advanced by t rows (128 B = 8 x 16 B); k: 16 bf16 = 32 B along the swizzle row
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(8 * t + 2 * k), idesc, acc);
+              acc = 1u;
+            }
+            umma_commit(emptya(sa));
+            if (++sa == C3_A_STAGES) {
+              sa = 0;
+              pha ^= 1u;
+            }
+          }
+          umma_commit(emptyb(sb));
+          if (++sb == C3_B_STAGES) {
+            sb = 0;
+            phb ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..17) ===========================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
+    const int sub = ew >> 2;       // the four warps of a quarter take every fourth column chunk
+    const int cl = quarter * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
+    const int hb = p.nb >> 1;              // breaths per half
+    const int n_valid = p.nb * lp - 2;     // columns that can carry an output
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int co0 = (tile % p.n_co_tiles) * TC_BLOCK_M, n0 = (tile / p.n_co_tiles) * p.nb;
+      mbar_wait(tfull_bar(buf), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * TC_MAX_N;
+      for (int h = 0; h < 2; ++h) {
+        // staging buffer h was last read by the store of this half of the PREVIOUS tile: at most one newer store
+        // (the other half) may still be in flight
+        if (leader) tma_store_wait_read_1();
+        named_bar_sync(1, C3_EPI_THREADS);
+        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_gen + (staging - smem_base) + h * C3_STAGING_BYTES);
+        const int j_lo = h * hb * lp;
+        int j_hi = (h + 1) * hb * lp;
+        if (j_hi > n_valid) j_hi = n_valid;
+        for (int ch = (j_lo >> 4) + sub; (ch << 4) < j_hi; ch += C3_EPI_WARPS / 4) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)(ch << 4), v);
+          tmem_ld_wait();
+          const int j0 = ch << 4;
+          int b = j0 / lp, q = j0 - b * lp;
+          __nv_bfloat16* dst = stg + ((b - h * hb) * p.l + q) * TC_BLOCK_M + cl;
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int j = j0 + jj;
+            if (j >= j_lo && j < j_hi && q < p.l) *dst = __float2bfloat16_rn(__uint_as_float(v[jj]));
+            dst += TC_BLOCK_M;
+            if (++q == lp) {  // next breath: the two straddling columns have no row in the compact staging tile
+              q = 0;
+              dst -= 2 * TC_BLOCK_M;
+            }
+          }
+        }
+        if (h == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(buf));  // TMEM buffer may be overwritten by the next-but-one tile
+        }
+        fence_proxy_async();
+        named_bar_sync(1, C3_EPI_THREADS);
+        if (leader) {
+          const uint32_t src = staging + h * C3_STAGING_BYTES;
+          if (p.accumulate) tma_reduce_add_4d(&tm_o, src, co0, 0, 0, n0 + h * hb);
+          else tma_store_4d(&tm_o, src, co0, 0, 0, n0 + h * hb);
+          tma_store_commit();
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -329,6 +574,16 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
   DARDS_CHECK_ARG(p.nb > 0 && n_tile % 16 == 0 && n_tile <= TC_MAX_N && n_tile >= 16,
                   "tcgen05 conv: unsupported position tile (%d breaths x %d)", p.nb, p.l_tile);
   DARDS_CHECK_ARG(p.n_taps > 0, "tcgen05 conv: no taps");
+  // Long reductions are LOAD-LATENCY bound with 3 stages (a stage is consumed in 448 cycles, a TMA load takes ~1 us:
+  // measured 59 % tensor-pipe activity): give them a 4th stage, paid for by storing the tile in two halves through a
+  // half-size staging buffer.  Short reductions are epilogue-bound and keep the one-store epilogue.
+  const int k_steps_total = p.n_taps * ceil_div(q.c_red, TC_BLOCK_K);
+  p.stages = 3;
+  p.halves = 1;
+  if (k_steps_total >= 12 && p.nb % 2 == 0 && (g_dbg_stages < 0 || g_dbg_stages == 4)) {
+    p.stages = 4;
+    p.halves = 2;
+  }
   CUtensorMap tm_w, tm_x, tm_o;
   {
     cuuint64_t dims[3] = {(cuuint64_t)q.c_red, (cuuint64_t)q.c_cols, (cuuint64_t)q.ktaps_total};
@@ -351,7 +606,7 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)q.c_cols, (cuuint64_t)planes, (cuuint64_t)l_plane, (cuuint64_t)q.n_breaths};
     cuuint64_t str[3] = {(cuuint64_t)q.dst_stride * 2, (cuuint64_t)q.dst_stride * planes * 2,
                          (cuuint64_t)q.dst_stride * q.l_dst * 2};
-    cuuint32_t box[4] = {TC_BLOCK_M, 1, (cuuint32_t)p.l_tile, (cuuint32_t)p.nb};
+    cuuint32_t box[4] = {TC_BLOCK_M, 1, (cuuint32_t)p.l_tile, (cuuint32_t)(p.nb / p.halves)};
     int rc = make_bf16_map(&tm_o, q.dst, 4, dims, str, box, false);
     if (rc) return rc;
   }
@@ -365,23 +620,94 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
   p.tma_epilogue = g_dbg_epilogue >= 0 ? g_dbg_epilogue : 1;
   p.n_pos_tiles = ceil_div(q.n_breaths, p.nb);
   p.n_co_tiles = ceil_div(q.c_cols, TC_BLOCK_M);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  const int smem_bytes = tc_smem_bytes(p.stages, p.halves);
+  static int attr_smem[2] = {0, 0};
+  if (smem_bytes > attr_smem[p.halves - 1]) {
+    cudaError_t e = p.halves == 1 ? cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                                  : cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
-      set_error("tcgen05 conv: cannot opt in to %d bytes of shared memory: %s", TC_SMEM_BYTES, cudaGetErrorString(e));
+      set_error("tcgen05 conv: cannot opt in to %d bytes of shared memory: %s", smem_bytes, cudaGetErrorString(e));
       return DARDS_ERR_CUDA;
     }
-    attr_set = true;
+    attr_smem[p.halves - 1] = smem_bytes;
   }
   const int tiles = p.n_pos_tiles * p.n_co_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   const uint32_t lbo = g_dbg_lbo >= 0 ? (uint32_t)g_dbg_lbo : 1u;
   const uint32_t sbo = g_dbg_sbo >= 0 ? (uint32_t)g_dbg_sbo : (1024u >> 4);
   const uint32_t ver = g_dbg_version >= 0 ? (uint32_t)g_dbg_version : 1u;
-  tc_conv_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tm_w, tm_x, tm_o, static_cast<__nv_bfloat16*>(q.dst), p, lbo,
-                                                          sbo, ver);
+  if (p.halves == 1)
+    tc_conv_kernel<1><<<grid, TC_THREADS, smem_bytes, st>>>(tm_w, tm_x, tm_o, static_cast<__nv_bfloat16*>(q.dst), p, lbo, sbo,
+                                                            ver);
+  else
+    tc_conv_kernel<2><<<grid, TC_THREADS, smem_bytes, st>>>(tm_w, tm_x, tm_o, static_cast<__nv_bfloat16*>(q.dst), p, lbo, sbo,
+                                                            ver);
   DARDS_CHECK_LAUNCH("tc_conv");
+  return DARDS_OK;
+}
+
+// v3 launch for k=3, s=1, p=1 (see tc_conv3_kernel).  `reverse_taps`: dgrad (tap s uses weight tap 2-s).
+static bool tc3_applicable(int l, int ktaps, int stride, int pad) {
+  if (g_dbg_conv3 != 1) return false;  // measured: no faster than the one-load-per-tap kernel; opt-in
+  return ktaps == 3 && stride == 1 && pad == 1 && 2 * (l + 2) <= C3_MAX_ROWS && l >= 2;
+}
+
+static int tc3_launch(const void* src, const void* w, void* dst, int n_breaths, int l, int c_red, int c_cols,
+                      int src_stride, int dst_stride, bool reverse_taps, bool accumulate, cudaStream_t st) {
+  DARDS_CHECK_ARG(c_red % 8 == 0 && src_stride % 8 == 0 && dst_stride % 8 == 0,
+                  "tcgen05 conv: channels/strides must be multiples of 8");
+  DARDS_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                  "tcgen05 conv: operands must be 16-byte aligned");
+  if (n_breaths == 0) return DARDS_OK;
+  TcConv3Params p{};
+  int nb = C3_MAX_ROWS / (l + 2);
+  nb &= ~1;  // the epilogue stores two halves of nb/2 breaths
+  if ((nb >> 1) * l > 128) nb = 2 * (128 / l);  // a half must fit the staging buffer (128 compact rows)
+  DARDS_CHECK_ARG(nb >= 2, "tcgen05 conv v3: sequence length %d too long for one tile", l);
+  p.nb = nb;
+  p.l = l;
+  p.n_cols = ((nb * (l + 2) - 2 + 15) / 16) * 16;
+  p.k_chunks = ceil_div(c_red, TC_BLOCK_K);
+  p.n_pos_tiles = ceil_div(n_breaths, nb);
+  p.n_co_tiles = ceil_div(c_cols, TC_BLOCK_M);
+  p.accumulate = accumulate ? 1 : 0;
+  for (int t = 0; t < 3; ++t) p.w_tap[t] = reverse_taps ? 2 - t : t;
+  CUtensorMap tm_w, tm_x, tm_o;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)c_red, (cuuint64_t)c_cols, 3};
+    cuuint64_t str[2] = {(cuuint64_t)c_red * 2, (cuuint64_t)c_red * c_cols * 2};
+    cuuint32_t box[3] = {TC_BLOCK_K, TC_BLOCK_M, 1};
+    int rc = make_bf16_map(&tm_w, w, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)c_red, 1, (cuuint64_t)l, (cuuint64_t)n_breaths};
+    cuuint64_t str[3] = {(cuuint64_t)src_stride * 2, (cuuint64_t)src_stride * 2, (cuuint64_t)src_stride * l * 2};
+    cuuint32_t box[4] = {TC_BLOCK_K, 1, (cuuint32_t)(l + 2), (cuuint32_t)nb};
+    int rc = make_bf16_map(&tm_x, src, 4, dims, str, box, true);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)c_cols, 1, (cuuint64_t)l, (cuuint64_t)n_breaths};
+    cuuint64_t str[3] = {(cuuint64_t)dst_stride * 2, (cuuint64_t)dst_stride * 2, (cuuint64_t)dst_stride * l * 2};
+    cuuint32_t box[4] = {TC_BLOCK_M, 1, (cuuint32_t)l, (cuuint32_t)(nb >> 1)};
+    int rc = make_bf16_map(&tm_o, dst, 4, dims, str, box, false);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("tcgen05 conv v3: cannot opt in to %d bytes of shared memory: %s", C3_SMEM_BYTES, cudaGetErrorString(e));
+      return DARDS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int tiles = p.n_pos_tiles * p.n_co_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  tc_conv3_kernel<<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(tm_w, tm_x, tm_o, p);
+  DARDS_CHECK_LAUNCH("tc_conv3");
   return DARDS_OK;
 }
 
@@ -394,6 +720,8 @@ int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend
     set_error("tcgen05 conv: the addend must be the output itself (in-place accumulation)");
     return DARDS_ERR_UNSUPPORTED;
   }
+  if (tc3_applicable(l_in, ktaps, stride, pad) && l_in == l_out)
+    return tc3_launch(in, w_koi, out, n_breaths, l_in, c_in, c_out, in_stride, out_stride, false, addend != nullptr, st);
   TcProblem q{};
   q.src = in; q.w = w_koi; q.dst = out;
   q.n_breaths = n_breaths; q.l_src = l_in; q.src_planes = stride; q.l_dst = l_out; q.dst_planes = 1;
@@ -426,6 +754,8 @@ int tc_conv_dgrad(const void* dout, const void* w_kio, void* din, const void* ad
     set_error("tcgen05 dgrad: the addend must be the output itself (in-place accumulation)");
     return DARDS_ERR_UNSUPPORTED;
   }
+  if (tc3_applicable(l_in, ktaps, stride, pad))
+    return tc3_launch(dout, w_kio, din, n_breaths, l_in, c_out, c_in, dout_stride, din_stride, true, addend != nullptr, st);
   // din[p = stride*m + r] = sum over taps t with (r + pad - t) % stride == 0 of dout[m + (r+pad-t)/stride] * W_t:
   // one launch per output parity plane r; reduction over c_out.
   for (int r = 0; r < stride; ++r) {
@@ -465,6 +795,8 @@ int tc_debug_set(int key, int value) {
   else if (key == 2) g_dbg_sbo = value;
   else if (key == 3) g_dbg_base_offset_mode = value;
   else if (key == 4) g_dbg_epilogue = value;
+  else if (key == 5) g_dbg_conv3 = value;
+  else if (key == 6) g_dbg_stages = value;
   else {
     set_error("tc_debug_set: unknown key %d", key);
     return DARDS_ERR_INVALID_ARGUMENT;

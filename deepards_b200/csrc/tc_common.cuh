@@ -8,7 +8,7 @@
 namespace dards {
 
 // debugging overrides of descriptor fields (dards_tc_debug_set); < 0 = default
-extern int g_dbg_lbo, g_dbg_version, g_dbg_sbo, g_dbg_base_offset_mode, g_dbg_epilogue;
+extern int g_dbg_lbo, g_dbg_version, g_dbg_sbo, g_dbg_base_offset_mode, g_dbg_epilogue, g_dbg_conv3, g_dbg_stages;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +83,8 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, uint32_t
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent bulk group have finished reading their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- TMEM / tcgen05 ----------------------------------------------------------------------------------

@@ -152,6 +152,37 @@ def test_conv_tcgen05_direct_store_epilogue_matches_tma_store():
     assert torch.equal(y_tma, y_direct)
 
 
+@pytest.mark.parametrize("case", [(40, 64, 64, 56, 3, 1, 1), (45, 128, 128, 28, 3, 1, 1), (70, 256, 256, 14, 3, 1, 1),
+                                  (61, 512, 512, 7, 3, 1, 1), (20, 128, 32, 14, 3, 1, 1), (9, 96, 160, 20, 3, 1, 1),
+                                  (1, 64, 64, 56, 3, 1, 1), (1030, 64, 64, 7, 3, 1, 1)])
+def test_conv_tcgen05_three_tap_single_load_kernel(case):
+    """Opt-in k3/s1/p1 kernel with ONE staged activation tile for the three taps (halo rows + row-shifted descriptors)
+    against the default one-load-per-tap kernel (3- and 4-stage variants, whole- and half-tile epilogues), forward,
+    dgrad and in-place dgrad; ragged breath counts (partial last tile), channel counts that are not tile multiples."""
+    from deepards_b200 import _lib
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 12)
+    xb, dyb = cl(x.bfloat16()), cl(dy.bfloat16())
+    add = torch.randn(n, l, cin, device=DEV).bfloat16()
+    y2 = K().conv1d_fwd(xb, w, s, p, impl=1)
+    d2 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1)
+    a2 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add)
+    _lib.call("dards_tc_debug_set", 5, 1)  # opt in to the single-load kernel
+    try:
+        y3 = K().conv1d_fwd(xb, w, s, p, impl=1)
+        d3 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1)
+        a3 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add)
+    finally:
+        _lib.call("dards_tc_debug_set", 5, -1)
+    torch.cuda.synchronize()
+    ref = cl(F.conv1d(xb.permute(0, 2, 1).float(), w.bfloat16().float(), stride=s, padding=p))
+    assert rel_err(y3.float(), ref) < 6e-3
+    # fp32 accumulation order differs (tap-major vs chunk-major): at most one bf16 ulp
+    assert rel_err(y3.float(), y2.float()) < 8e-3
+    assert rel_err(d3.float(), d2.float()) < 8e-3
+    assert rel_err(a3.float(), a2.float()) < 1.6e-2
+
+
 WGRAD_CASES = [c for c in CONV_CASES[:9]] + [(256, 64, 64, 56, 3, 1, 1), (37, 128, 256, 28, 3, 2, 1)]
 
 
