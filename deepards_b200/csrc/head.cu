@@ -81,19 +81,30 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
   return (uint32_t)(z >> 32);
 }
 
-template <typename T>
+// VEC consecutive channels per thread (a 16-byte access when the slice allows it, else scalar); the random number of
+// an element depends only on (seed, row * c + channel), never on the vector width.
+template <typename T, int VEC>
 __global__ void dropout_kernel(T* __restrict__ x, long long n_rows, int c, int stride, float p, float scale,
                                unsigned long long seed, const unsigned long long* __restrict__ seed_off) {
   if (seed_off) seed += *seed_off * 0x9E3779B97F4A7C15ull;
-  long long total = n_rows * c;
+  const int cv = c / VEC;
+  const long long total = n_rows * cv;
   const uint32_t thresh = (uint32_t)(p * 4294967296.0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / c;
-    int cc = (int)(i % c);
+    const long long r = i / cv;
+    const int cc = (int)(i % cv) * VEC;
     T* ptr = x + (size_t)r * stride + cc;
-    uint32_t rnd = mix32(seed ^ ((uint64_t)i * 0xD1342543DE82EF95ull));
-    float v = Elem<T>::ld(ptr);
-    Elem<T>::st(ptr, rnd < thresh ? 0.f : v * scale);
+    T v[VEC];
+    if (VEC > 1) *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(ptr);
+    else v[0] = *ptr;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const uint32_t rnd = mix32(seed ^ ((uint64_t)(r * c + cc + j) * 0xD1342543DE82EF95ull));
+      const float f = Elem<T>::ld(&v[j]);
+      Elem<T>::st(&v[j], rnd < thresh ? 0.f : f * scale);
+    }
+    if (VEC > 1) *reinterpret_cast<uint4*>(ptr) = *reinterpret_cast<const uint4*>(v);
+    else *ptr = v[0];
   }
 }
 
@@ -269,9 +280,15 @@ int launch_dropout(void* x, int n_rows, int c, int stride, float p, unsigned lon
                    const unsigned long long* seed_off, int dtype, cudaStream_t st) {
   DARDS_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
   if (n_rows == 0 || p == 0.f) return DARDS_OK;
-  int blocks = grid_for((long long)n_rows * c, 256);
   DARDS_DISPATCH_DTYPE(dtype, {
-    dropout_kernel<T><<<blocks, 256, 0, st>>>(static_cast<T*>(x), n_rows, c, stride, p, 1.f / (1.f - p), seed, seed_off);
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const bool vec_ok = c % VEC == 0 && stride % VEC == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (vec_ok)
+      dropout_kernel<T, VEC><<<grid_for((long long)n_rows * (c / VEC), 256), 256, 0, st>>>(
+          static_cast<T*>(x), n_rows, c, stride, p, 1.f / (1.f - p), seed, seed_off);
+    else
+      dropout_kernel<T, 1><<<grid_for((long long)n_rows * c, 256), 256, 0, st>>>(static_cast<T*>(x), n_rows, c, stride, p,
+                                                                                 1.f / (1.f - p), seed, seed_off);
   })
   DARDS_CHECK_LAUNCH("dropout");
   return DARDS_OK;

@@ -28,6 +28,7 @@ constexpr int WG_CHUNK_B = (WG_RMAX + 8) * 128;    // input tile: + 8 zero rows 
 constexpr int WG_A_BYTES = 2 * WG_CHUNK_A;         // 128 output channels
 constexpr int WG_B_BYTES = 2 * WG_CHUNK_B;         // 128 input channels
 constexpr int WG_MAX_TAPS = 3;
+constexpr int WG_MAX_STAGES = 8;
 constexpr int WG_SMEM_LIMIT = 227 * 1024;
 
 struct WgTcParams {
@@ -44,6 +45,7 @@ struct WgTcParams {
   int c_in, c_out;
   int n_ci_tiles, n_co_tiles;
   int stages, stage_bytes;
+  int a_bytes, b_bytes;        // bytes of the dout tile / of one input tile inside a stage (1 or 2 64-channel chunks)
   int base_offset_mode;        // 1 (default): base_offset 0;  0: (start >> 7) & 7 -- kept for the probe only
 };
 
@@ -55,9 +57,9 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + p.stages * p.stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
-  const uint32_t done_bar = bar_base + 8u * 8;
-  const uint32_t tmem_slot = bar_base + 8u * 9;
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WG_MAX_STAGES + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * WG_MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WG_MAX_STAGES + 1);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
         mbar_arrive_expect_tx(full_bar(stage), tx);
         for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * WG_CHUNK_A, &tm_a, full_bar(stage), co0 + c * 64, 0, p.a_start, n0);
         for (int b = 0; b < p.n_btiles; ++b) {
-          const uint32_t sb = sa + WG_A_BYTES + b * WG_B_BYTES;
+          const uint32_t sb = sa + p.a_bytes + b * p.b_bytes;
           for (int c = 0; c < ci_chunks; ++c)
             tma_load_4d(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0);
         }
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       uint32_t d_tmem[WG_MAX_TAPS];
 #pragma unroll
       for (int t = 0; t < WG_MAX_TAPS; ++t) {
-        const uint32_t off = WG_A_BYTES + p.tap_btile[t] * WG_B_BYTES + p.tap_shift[t] * 128;
+        const uint32_t off = p.a_bytes + p.tap_btile[t] * p.b_bytes + p.tap_shift[t] * 128;
         const uint32_t bo = p.base_offset_mode == 0 ? (uint32_t)(p.tap_shift[t] & 7) : 0u;
         b_tmpl[t] = make_sw128_desc(0, WG_CHUNK_B >> 4, 1024 >> 4, 1, bo) + (uint64_t)(off >> 4);
         d_tmem[t] = tmem_base + (uint32_t)t * 128u;
@@ -290,9 +292,13 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   p.c_in = c_in; p.c_out = c_out;
   p.n_ci_tiles = ceil_div(c_in, 128);
   p.n_co_tiles = ceil_div(c_out, 128);
-  p.stage_bytes = WG_A_BYTES + p.n_btiles * WG_B_BYTES;
+  // a stage holds 1 or 2 64-channel chunks of each operand: narrow layers get a deeper ring out of the same shared
+  // memory (they are load-latency bound: the reduction streams activations straight from HBM)
+  p.a_bytes = (c_out > 64 ? 2 : 1) * WG_CHUNK_A;
+  p.b_bytes = (c_in > 64 ? 2 : 1) * WG_CHUNK_B;
+  p.stage_bytes = p.a_bytes + p.n_btiles * p.b_bytes;
   p.stages = (WG_SMEM_LIMIT - 2048) / p.stage_bytes;
-  if (p.stages > 4) p.stages = 4;
+  if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
   if (p.stages < 2) return w;
   const int tiles = p.n_ci_tiles * p.n_co_tiles;
   // exactly one wave: tiles * splits <= #SMs (1 CTA per SM: ~200 KB of shared memory each), so no tail wave
