@@ -239,27 +239,44 @@ __global__ void __launch_bounds__(THREADS)
   uint4* cache_m = cache + (size_t)2 * K * THREADS;
   const bool use_mask = relu_mode == 2;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-  // element offset of this thread's channel vector in row 0 of the tile (in units of rows*stride + c0), or -1
   auto tile_c0 = [&](int tile) { return (tile % n_ct) * CT + cq * V; };
-  auto issue_row = [&](int tile, int k, int r) {
-    const size_t row = (size_t)(tile / n_ct) * rows + r;
+  // per-tile base pointers of this thread's channel vector (row 0 of the group), computed ONCE per tile: the row loops
+  // below only add r * stride (the tile -> (group, channel tile) division must not sit in the per-row path)
+  struct TilePtrs {
+    const T* g;
+    const T* x;
+    const T* m;
+  };
+  auto tile_ptrs = [&](int tile) {
+    const size_t row0 = (size_t)(tile / n_ct) * rows;
     const int c0 = tile_c0(tile);
-    cp_async16(&cache_g[k * THREADS + threadIdx.x], dout + row * dout_stride + c0);
-    cp_async16(&cache_x[k * THREADS + threadIdx.x], x + row * x_stride + c0);
-    if (use_mask) cp_async16(&cache_m[k * THREADS + threadIdx.x], mask_src + row * mask_stride + c0);
+    TilePtrs tp;
+    tp.g = dout + row0 * dout_stride + c0;
+    tp.x = x + row0 * x_stride + c0;
+    tp.m = use_mask ? mask_src + row0 * mask_stride + c0 : nullptr;
+    return tp;
+  };
+  auto issue_row = [&](const TilePtrs& tp, int k, int r) {
+    const int slot = k * THREADS + threadIdx.x;
+    cp_async16(&cache_g[slot], tp.g + (size_t)r * dout_stride);
+    cp_async16(&cache_x[slot], tp.x + (size_t)r * x_stride);
+    if (use_mask) cp_async16(&cache_m[slot], tp.m + (size_t)r * mask_stride);
   };
   int tile = blockIdx.x;
-  if (tile < n_tiles && tile_c0(tile) < c)
+  if (tile < n_tiles && tile_c0(tile) < c) {
+    const TilePtrs tp = tile_ptrs(tile);
     for (int k = 0; k < K; ++k) {
       const int r = rl + k * LANES;
-      if (r < rows) issue_row(tile, k, r);
+      if (r < rows) issue_row(tp, k, r);
     }
+  }
   for (; tile < n_tiles; tile += gridDim.x) {
     const int g = tile / n_ct, c0 = tile_c0(tile);
     const bool active = c0 < c;
     const size_t row_base = (size_t)g * rows;
     const int next = tile + gridDim.x;
     const bool refill = next < n_tiles && tile_c0(next) < c;
+    const TilePtrs tp_next = refill ? tile_ptrs(next) : TilePtrs{nullptr, nullptr, nullptr};
     float mean[V], rstd[V], sc[V], sh[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(THREADS)
         const int k = k0 + u, r = rl + k * LANES;
         if (r < rows) {
           const uint4 rg = cache_g[k * THREADS + threadIdx.x], rx = cache_x[k * THREADS + threadIdx.x];
-          if (refill) issue_row(next, k, r);
+          if (refill) issue_row(tp_next, k, r);
           if (active) {
             float gv[V], xv[V], o[V];
             Vec<T>::unpack(rg, gv);

@@ -28,6 +28,11 @@ SEQ_LEN = 224
 _DTYPES = {"fp32": (torch.float32, _lib.F32), "bf16": (torch.bfloat16, _lib.BF16)}
 
 
+def _multi_rank():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def default_precision():
     return os.environ.get("DEEPARDS_B200_PRECISION", "fp32")
 
@@ -146,8 +151,11 @@ class Plan(object):
 
     def mark(self, first_param):
         """Backward bookkeeping for the overlapped all-reduce: every gradient slot at or after `first_param`'s
-        is final once the calls recorded so far have run (backward visits the layers last to first)."""
-        self._flush_reductions()
+        is final once the calls recorded so far have run (backward visits the layers last to first).
+        With more than one rank the pending partial-sum reductions are flushed here, so that the bucket behind the mark
+        can go to the all-reduce; a single rank reduces everything in ONE launch at the end of the backward."""
+        if _multi_rank():
+            self._flush_reductions()
         self.bwd_marks.append((self.goff[id(first_param)], len(self.bwd.calls)))
 
     def grad_view(self, p):

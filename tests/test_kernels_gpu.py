@@ -183,7 +183,11 @@ def test_conv_tcgen05_three_tap_single_load_kernel(case):
     assert rel_err(a3.float(), a2.float()) < 1.6e-2
 
 
-WGRAD_CASES = [c for c in CONV_CASES[:9]] + [(256, 64, 64, 56, 3, 1, 1), (37, 128, 256, 28, 3, 2, 1)]
+WGRAD_CASES = [c for c in CONV_CASES[:9]] + [(256, 64, 64, 56, 3, 1, 1), (37, 128, 256, 28, 3, 2, 1),
+                                             # BASELINE batch (5120 breaths): one wave of split-K CTAs
+                                             (5120, 512, 512, 7, 3, 1, 1), (5120, 256, 256, 14, 3, 1, 1),
+                                             (5120, 64, 64, 56, 3, 1, 1), (5120, 256, 512, 14, 3, 2, 1),
+                                             (5120, 128, 256, 28, 1, 2, 0), (2000, 128, 32, 14, 3, 1, 1)]
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
@@ -196,6 +200,7 @@ def test_conv_tcgen05_wgrad(case):
     got = K().conv1d_wgrad(xb, dyb, k, s, p, impl=1)
     torch.cuda.synchronize()
     assert rel_err(got, ref) < 2e-4, rel_err(got, ref)  # both accumulate exact bf16 products in fp32
+    assert torch.equal(got, K().conv1d_wgrad(xb, dyb, k, s, p, impl=1))  # deterministic (fixed-order split-K reduction)
 
 
 def test_conv_tcgen05_into_channel_slice():

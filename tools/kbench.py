@@ -137,6 +137,13 @@ def stem():
     print("stem bwd: %6.1f us" % timeit(b), flush=True)
 
 
+def convprof():
+    """two small-layer conv launches (fwd) and one wgrad for `ncu --set full -k regex:tc_`"""
+    global SHAPES, ROT
+    SHAPES, ROT = [(64, 56)], 2
+    conv()
+
+
 def bnprof():
     """a handful of BN launches for `ncu --set full -k regex:gbn`"""
     global SHAPES, ROT
@@ -148,5 +155,7 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["bn", "conv", "stem"]
     torch.cuda.set_device(0)
     _lib.load()
+    if os.environ.get("KBENCH_CLUSTER"):
+        _lib.call("dards_tc_debug_set", 8, int(os.environ["KBENCH_CLUSTER"]))
     for wname in what:
-        {"bn": bn, "conv": conv, "stem": stem, "bnprof": bnprof}[wname]()
+        {"bn": bn, "conv": conv, "stem": stem, "bnprof": bnprof, "convprof": convprof}[wname]()
