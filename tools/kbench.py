@@ -137,6 +137,20 @@ def stem():
     print("stem bwd: %6.1f us" % timeit(b), flush=True)
 
 
+def copy():
+    """the practical floor: torch's elementwise copy / read-only reduction of one 36.7 MB activation tensor, same rotation"""
+    for mb, shape in ((36.7, (5120, 56, 64)), (147, (4 * 5120, 56, 64))):
+        xs = [torch.randn(*shape, device=DEV).to(BF) for _ in range(ROT)]
+        outs = [torch.empty_like(x) for x in xs]
+        t = timeit(lambda i: outs[i % ROT].copy_(xs[i % ROT]))
+        print("torch copy   %6.1f MB: %6.1f us  %5.0f GB/s (r+w)" % (mb, t, 2 * mb / t * 1e3))
+        t = timeit(lambda i: outs[i % ROT].copy_(outs[i % ROT]) if False else torch.add(xs[i % ROT], 1, out=outs[i % ROT]))
+        print("torch add    %6.1f MB: %6.1f us  %5.0f GB/s (r+w)" % (mb, t, 2 * mb / t * 1e3))
+        acc = torch.zeros(shape[-1], device=DEV, dtype=torch.float32)
+        t = timeit(lambda i: torch.sum(xs[i % ROT], dim=(0, 1), dtype=torch.float32, out=acc))
+        print("torch sum    %6.1f MB: %6.1f us  %5.0f GB/s (read only)" % (mb, t, mb / t * 1e3), flush=True)
+
+
 def convprof():
     """two small-layer conv launches (fwd) and one wgrad for `ncu --set full -k regex:tc_`"""
     global SHAPES, ROT
@@ -155,7 +169,9 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["bn", "conv", "stem"]
     torch.cuda.set_device(0)
     _lib.load()
-    if os.environ.get("KBENCH_CLUSTER"):
-        _lib.call("dards_tc_debug_set", 8, int(os.environ["KBENCH_CLUSTER"]))
+    if os.environ.get("KBENCH_CONV3"):
+        _lib.call("dards_tc_debug_set", 5, int(os.environ["KBENCH_CONV3"]))  # opt in to the single-load 3-tap kernel
+    if os.environ.get("KBENCH_STAGES"):
+        _lib.call("dards_tc_debug_set", 6, int(os.environ["KBENCH_STAGES"]))
     for wname in what:
-        {"bn": bn, "conv": conv, "stem": stem, "bnprof": bnprof, "convprof": convprof}[wname]()
+        {"bn": bn, "conv": conv, "stem": stem, "bnprof": bnprof, "convprof": convprof, "copy": copy}[wname]()
