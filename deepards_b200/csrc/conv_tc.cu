@@ -279,18 +279,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 // q >= L straddle two breaths; they are computed and dropped (2 of every L+2 columns).
 // Versus one load per tap this cuts the shared-memory fill per MMA from (A+B) to (A + B/3): an SS-mode tcgen05.mma
 // already reads (M+N)*32 B per K=16 step, and TMA writes + MMA reads share the SM's 128 B/clk.
-// Two rings: activation tiles (one per 64-channel chunk, 3 stages) and weight tiles (one per chunk and tap, 4 stages).
-// The epilogue writes the tile in two halves of NB/2 breaths, each through its own 32 KB staging buffer, so the
-// TMEM -> shared transposition of one half overlaps the TMA store of the other.
-constexpr int C3_B_STAGES = 2;
-constexpr int C3_A_STAGES = 4;
-constexpr int C3_EPI_WARPS = 16;  // 4 per TMEM lane quarter: the epilogue is 2-byte shared-memory stores, it needs warps
+// Two rings: activation tiles (one per 64-channel chunk, 3 stages = up to 3 TILES of look-ahead on the narrow layers,
+// which are load-latency bound) and weight tiles (one per chunk and tap, 3 stages).
+// The epilogue is the wide kernel's: every accumulator column j goes to staging row j (the straddling columns too),
+// then one TMA store per breath reads its L rows out of the staging tile.
+constexpr int C3_B_STAGES = 3;
+constexpr int C3_A_STAGES = 3;
+constexpr int C3_EPI_WARPS = 8;
 constexpr int C3_EPI_THREADS = C3_EPI_WARPS * 32;
 constexpr int C3_THREADS = 64 + C3_EPI_THREADS;
 constexpr int C3_MAX_ROWS = 258;                                       // staged rows read by the MMAs (N <= 256, + 2)
 constexpr int C3_B_BYTES = ((C3_MAX_ROWS * 128 + 1023) / 1024) * 1024;  // 33 KB
-constexpr int C3_STAGING_BYTES = 128 * 128 * 2;                        // <= 128 compact rows x 128 channels, bf16
-constexpr int C3_SMEM_BYTES = C3_B_STAGES * C3_B_BYTES + C3_A_STAGES * TC_A_BYTES + 2 * C3_STAGING_BYTES + 1024 + 256;
+constexpr int C3_STAGING_BYTES = 256 * 128 * 2;                        // one row per MMA column x 128 channels, bf16
+constexpr int C3_SMEM_BYTES = C3_B_STAGES * C3_B_BYTES + C3_A_STAGES * TC_A_BYTES + C3_STAGING_BYTES + 1024 + 256;
 
 struct TcConv3Params {
   int w_tap[3];   // weight tap used with a row shift of 0, 1, 2
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
   const uint32_t b_base = smem_base;
   const uint32_t a_base = b_base + C3_B_STAGES * C3_B_BYTES;
   const uint32_t staging = a_base + C3_A_STAGES * TC_A_BYTES;
-  const uint32_t bar_base = staging + 2 * C3_STAGING_BYTES;
+  const uint32_t bar_base = staging + C3_STAGING_BYTES;
   auto fullb = [&](int s) { return bar_base + 8u * s; };
   auto emptyb = [&](int s) { return bar_base + 8u * (C3_B_STAGES + s); };
   auto fulla = [&](int s) { return bar_base + 8u * (2 * C3_B_STAGES + s); };
@@ -424,14 +425,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
       }
     }
   } else {
-    // =========================== epilogue (warps 2..17) ===========================
+    // =========================== epilogue (warps 2..9) ===========================
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
-    const int sub = ew >> 2;       // the four warps of a quarter take every fourth column chunk
+    const int sub = ew >> 2;       // the two warps of a quarter alternate over the column chunks
     const int cl = quarter * 32 + lane;
     const bool leader = (threadIdx.x == 64);
-    const int hb = p.nb >> 1;              // breaths per half
-    const int n_valid = p.nb * lp - 2;     // columns that can carry an output
+    const int n_chunks = p.n_cols >> 4;
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_gen + (staging - smem_base));
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -439,46 +440,28 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
       mbar_wait(tfull_bar(buf), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * TC_MAX_N;
-      for (int h = 0; h < 2; ++h) {
-        // staging buffer h was last read by the store of this half of the PREVIOUS tile: at most one newer store
-        // (the other half) may still be in flight
-        if (leader) tma_store_wait_read_1();
-        named_bar_sync(1, C3_EPI_THREADS);
-        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_gen + (staging - smem_base) + h * C3_STAGING_BYTES);
-        const int j_lo = h * hb * lp;
-        int j_hi = (h + 1) * hb * lp;
-        if (j_hi > n_valid) j_hi = n_valid;
-        for (int ch = (j_lo >> 4) + sub; (ch << 4) < j_hi; ch += C3_EPI_WARPS / 4) {
-          uint32_t v[16];
-          tmem_ld16(t_row + (uint32_t)(ch << 4), v);
-          tmem_ld_wait();
-          const int j0 = ch << 4;
-          int b = j0 / lp, q = j0 - b * lp;
-          __nv_bfloat16* dst = stg + ((b - h * hb) * p.l + q) * TC_BLOCK_M + cl;
+      if (leader) tma_store_wait_read();  // the previous tile's stores have finished reading the staging tile
+      named_bar_sync(1, C3_EPI_THREADS);
+      for (int ch = sub; ch < n_chunks; ch += 2) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)(ch << 4), v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const int j = j0 + jj;
-            if (j >= j_lo && j < j_hi && q < p.l) *dst = __float2bfloat16_rn(__uint_as_float(v[jj]));
-            dst += TC_BLOCK_M;
-            if (++q == lp) {  // next breath: the two straddling columns have no row in the compact staging tile
-              q = 0;
-              dst -= 2 * TC_BLOCK_M;
-            }
-          }
+        for (int j = 0; j < 16; ++j) stg[((ch << 4) + j) * TC_BLOCK_M + cl] = __float2bfloat16_rn(__uint_as_float(v[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));  // TMEM buffer may be overwritten by the next-but-one tile
+      fence_proxy_async();
+      named_bar_sync(1, C3_EPI_THREADS);
+      if (leader) {
+        // breath b = staging rows [b*(L+2), b*(L+2) + L); the TMA unit clips channels >= Cout and breaths >= N
+        for (int b = 0; b < p.nb; ++b) {
+          const uint32_t src = staging + (uint32_t)(b * lp * TC_BLOCK_M * 2);
+          if (p.accumulate) tma_reduce_add_4d(&tm_o, src, co0, 0, 0, n0 + b);
+          else tma_store_4d(&tm_o, src, co0, 0, 0, n0 + b);
         }
-        if (h == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(buf));  // TMEM buffer may be overwritten by the next-but-one tile
-        }
-        fence_proxy_async();
-        named_bar_sync(1, C3_EPI_THREADS);
-        if (leader) {
-          const uint32_t src = staging + h * C3_STAGING_BYTES;
-          if (p.accumulate) tma_reduce_add_4d(&tm_o, src, co0, 0, 0, n0 + h * hb);
-          else tma_store_4d(&tm_o, src, co0, 0, 0, n0 + h * hb);
-          tma_store_commit();
-        }
+        tma_store_commit();
       }
     }
     if (leader) tma_store_wait_all();
@@ -647,9 +630,13 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
 }
 
 // v3 launch for k=3, s=1, p=1 (see tc_conv3_kernel).  `reverse_taps`: dgrad (tap s uses weight tap 2-s).
-static bool tc3_applicable(int l, int ktaps, int stride, int pad) {
-  if (g_dbg_conv3 != 1) return false;  // measured: no faster than the one-load-per-tap kernel; opt-in
-  return ktaps == 3 && stride == 1 && pad == 1 && 2 * (l + 2) <= C3_MAX_ROWS && l >= 2;
+// Measured (profiles/r01_kbench_conv.txt): 21.6 vs 23.5 us at C = 64 and 22.4 vs 24.7 us at C = 128 -- the narrow layers
+// are load-latency bound and gain from 3 tiles of look-ahead; at C >= 256 the one-load-per-tap kernel with its 4-stage
+// ring is faster (no straddling columns: 32.0 vs 33.7 us, 50.8 vs 54.0 us).  dards_tc_debug_set(5, 0 | 1) forces it off | on.
+static bool tc3_applicable(int l, int c_red, int ktaps, int stride, int pad) {
+  if (g_dbg_conv3 == 0) return false;
+  if (!(ktaps == 3 && stride == 1 && pad == 1 && l + 2 <= C3_MAX_ROWS && l >= 2)) return false;
+  return g_dbg_conv3 == 1 || c_red <= 128;
 }
 
 static int tc3_launch(const void* src, const void* w, void* dst, int n_breaths, int l, int c_red, int c_cols,
@@ -661,10 +648,8 @@ static int tc3_launch(const void* src, const void* w, void* dst, int n_breaths, 
                   "tcgen05 conv: operands must be 16-byte aligned");
   if (n_breaths == 0) return DARDS_OK;
   TcConv3Params p{};
-  int nb = C3_MAX_ROWS / (l + 2);
-  nb &= ~1;  // the epilogue stores two halves of nb/2 breaths
-  if ((nb >> 1) * l > 128) nb = 2 * (128 / l);  // a half must fit the staging buffer (128 compact rows)
-  DARDS_CHECK_ARG(nb >= 2, "tcgen05 conv v3: sequence length %d too long for one tile", l);
+  const int nb = C3_MAX_ROWS / (l + 2);
+  DARDS_CHECK_ARG(nb >= 1, "tcgen05 conv v3: sequence length %d too long for one tile", l);
   p.nb = nb;
   p.l = l;
   p.n_cols = ((nb * (l + 2) - 2 + 15) / 16) * 16;
@@ -691,7 +676,7 @@ static int tc3_launch(const void* src, const void* w, void* dst, int n_breaths, 
   {
     cuuint64_t dims[4] = {(cuuint64_t)c_cols, 1, (cuuint64_t)l, (cuuint64_t)n_breaths};
     cuuint64_t str[3] = {(cuuint64_t)dst_stride * 2, (cuuint64_t)dst_stride * 2, (cuuint64_t)dst_stride * l * 2};
-    cuuint32_t box[4] = {TC_BLOCK_M, 1, (cuuint32_t)l, (cuuint32_t)(nb >> 1)};
+    cuuint32_t box[4] = {TC_BLOCK_M, 1, (cuuint32_t)l, 1};
     int rc = make_bf16_map(&tm_o, dst, 4, dims, str, box, false);
     if (rc) return rc;
   }
@@ -720,7 +705,7 @@ int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend
     set_error("tcgen05 conv: the addend must be the output itself (in-place accumulation)");
     return DARDS_ERR_UNSUPPORTED;
   }
-  if (tc3_applicable(l_in, ktaps, stride, pad) && l_in == l_out)
+  if (tc3_applicable(l_in, c_in, ktaps, stride, pad) && l_in == l_out)
     return tc3_launch(in, w_koi, out, n_breaths, l_in, c_in, c_out, in_stride, out_stride, false, addend != nullptr, st);
   TcProblem q{};
   q.src = in; q.w = w_koi; q.dst = out;
@@ -754,7 +739,7 @@ int tc_conv_dgrad(const void* dout, const void* w_kio, void* din, const void* ad
     set_error("tcgen05 dgrad: the addend must be the output itself (in-place accumulation)");
     return DARDS_ERR_UNSUPPORTED;
   }
-  if (tc3_applicable(l_in, ktaps, stride, pad))
+  if (tc3_applicable(l_in, c_out, ktaps, stride, pad))
     return tc3_launch(dout, w_kio, din, n_breaths, l_in, c_out, c_in, dout_stride, din_stride, true, addend != nullptr, st);
   // din[p = stride*m + r] = sum over taps t with (r + pad - t) % stride == 0 of dout[m + (r+pad-t)/stride] * W_t:
   // one launch per output parity plane r; reduction over c_out.

@@ -142,12 +142,14 @@ def test_conv_tcgen05_direct_store_epilogue_matches_tma_store():
     n, cin, cout, l, k, s, p = case
     x, w, _ = _conv_inputs(case, 6)
     xb = cl(x.bfloat16())
-    y_tma = K().conv1d_fwd(xb, w, s, p, impl=1)
-    _lib.call("dards_tc_debug_set", 4, 0)
+    _lib.call("dards_tc_debug_set", 5, 0)  # the one-load-per-tap kernel (the only one with a direct-store fallback)
     try:
+        y_tma = K().conv1d_fwd(xb, w, s, p, impl=1)
+        _lib.call("dards_tc_debug_set", 4, 0)
         y_direct = K().conv1d_fwd(xb, w, s, p, impl=1)
     finally:
         _lib.call("dards_tc_debug_set", 4, -1)
+        _lib.call("dards_tc_debug_set", 5, -1)
     torch.cuda.synchronize()
     assert torch.equal(y_tma, y_direct)
 
@@ -156,24 +158,23 @@ def test_conv_tcgen05_direct_store_epilogue_matches_tma_store():
                                   (61, 512, 512, 7, 3, 1, 1), (20, 128, 32, 14, 3, 1, 1), (9, 96, 160, 20, 3, 1, 1),
                                   (1, 64, 64, 56, 3, 1, 1), (1030, 64, 64, 7, 3, 1, 1)])
 def test_conv_tcgen05_three_tap_single_load_kernel(case):
-    """Opt-in k3/s1/p1 kernel with ONE staged activation tile for the three taps (halo rows + row-shifted descriptors)
-    against the default one-load-per-tap kernel (3- and 4-stage variants, whole- and half-tile epilogues), forward,
+    """k3/s1/p1 kernel with ONE staged activation tile for the three taps (halo rows + row-shifted descriptors)
+    against the one-load-per-tap kernel (3- and 4-stage variants, whole- and half-tile epilogues), forward,
     dgrad and in-place dgrad; ragged breath counts (partial last tile), channel counts that are not tile multiples."""
     from deepards_b200 import _lib
     n, cin, cout, l, k, s, p = case
     x, w, dy = _conv_inputs(case, 12)
     xb, dyb = cl(x.bfloat16()), cl(dy.bfloat16())
     add = torch.randn(n, l, cin, device=DEV).bfloat16()
-    y2 = K().conv1d_fwd(xb, w, s, p, impl=1)
-    d2 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1)
-    a2 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add)
-    _lib.call("dards_tc_debug_set", 5, 1)  # opt in to the single-load kernel
-    try:
-        y3 = K().conv1d_fwd(xb, w, s, p, impl=1)
-        d3 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1)
-        a3 = K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add)
-    finally:
-        _lib.call("dards_tc_debug_set", 5, -1)
+    outs = {}
+    for mode in (0, 1):  # 0: one load per tap (the wide-layer kernel), 1: single load (default for <= 128 channels)
+        _lib.call("dards_tc_debug_set", 5, mode)
+        try:
+            outs[mode] = (K().conv1d_fwd(xb, w, s, p, impl=1), K().conv1d_dgrad(dyb, w, l, s, p, impl=1),
+                          K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add))
+        finally:
+            _lib.call("dards_tc_debug_set", 5, -1)
+    (y2, d2, a2), (y3, d3, a3) = outs[0], outs[1]
     torch.cuda.synchronize()
     ref = cl(F.conv1d(xb.permute(0, 2, 1).float(), w.bfloat16().float(), stride=s, padding=p))
     assert rel_err(y3.float(), ref) < 6e-3
