@@ -19,7 +19,6 @@
 
 namespace dards {
 
-constexpr int BN_UNROLL = 3;  // rows in flight per thread in the global-memory sweeps of the cached kernels
 
 template <typename T> struct Vec;
 template <> struct Vec<float> {
@@ -100,39 +99,49 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // brought in with cp.async (no registers, the whole tile in flight at once); while the last sweep of tile i reads
 // row k out of the cache and stores its result, it refills slot k with row k of tile i+1 -- so the loads of the next
 // tile overlap the stores of the current one and an SM always has a full tile of requests outstanding.
-template <typename T, int VPR, int THREADS>
+// Row loops of the cached kernels: a thread owns rows rl, rl + LANES, ... of its channel vector.  All but the last
+// iteration are full (every lane has a row), so only the tail is guarded, and every pointer advances by a constant
+// per iteration -- per-row address arithmetic and bounds checks were a third of the instructions of these
+// (instruction-issue bound) kernels.
+template <typename F>
+__device__ __forceinline__ void bn_for_rows(int kf, bool tail, F&& body) {
+#pragma unroll 3
+  for (int k = 0; k < kf; ++k) body();
+  if (tail) body();
+}
+
+template <typename T, int VPR, int THREADS, bool HAS_RES, bool RELU>
 __global__ void __launch_bounds__(THREADS)
     gbn_fwd_cached_kernel(const T* x, T* out, const T* res, const float* __restrict__ gamma, const float* __restrict__ beta,
                           float* __restrict__ save_mean, float* __restrict__ save_rstd, int n_groups, int rows, int c,
-                          int x_stride, int out_stride, int res_stride, float eps, int relu) {
-  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V, U = BN_UNROLL;
+                          int x_stride, int out_stride, int res_stride, float eps) {
+  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V;
   extern __shared__ uint4 cache[];  // [K][THREADS]
   __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
   const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
   const float inv_n = 1.f / (float)rows;
-  const int K = (rows + LANES - 1) / LANES;
+  const int kf = rows / LANES;                 // full iterations
+  const bool tail = rl < rows - kf * LANES;    // this lane has a row in the last, partial iteration
   const int n_ct = (c + CT - 1) / CT;
   const int n_tiles = n_ct * n_groups;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-  // first element of this thread's channel vector in the tile, or nullptr past the last channel
+  const size_t x_step = (size_t)LANES * x_stride, o_step = (size_t)LANES * out_stride, r_step = (size_t)LANES * res_stride;
+  // this thread's first row (row lane rl) of its channel vector in the tile, or nullptr past the last channel
   auto tile_x = [&](int tile) -> const T* {
     const int c0 = (tile % n_ct) * CT + cq * V;
-    return c0 < c ? x + (size_t)(tile / n_ct) * rows * x_stride + c0 : nullptr;
+    return c0 < c ? x + ((size_t)(tile / n_ct) * rows + rl) * x_stride + c0 : nullptr;
   };
   int tile = blockIdx.x;
   if (tile < n_tiles) {
     const T* xp = tile_x(tile);
-    if (xp)
-      for (int k = 0; k < K; ++k) {
-        const int r = rl + k * LANES;
-        if (r < rows) cp_async16(&cache[k * THREADS + threadIdx.x], xp + (size_t)r * x_stride);
-      }
+    if (xp) {
+      uint4* slot = cache + threadIdx.x;
+      bn_for_rows(kf, tail, [&]() { cp_async16(slot, xp); slot += THREADS; xp += x_step; });
+    }
   }
   for (; tile < n_tiles; tile += gridDim.x) {
     const int g = tile / n_ct, c0 = (tile % n_ct) * CT + cq * V;
     const bool active = c0 < c;
-    const size_t row_base = (size_t)g * rows;
-    const T* xnext = tile + gridDim.x < n_tiles ? tile_x(tile + gridDim.x) : nullptr;
+    const T* xn = tile + gridDim.x < n_tiles ? tile_x(tile + gridDim.x) : nullptr;
     cp_async_wait_all();
     __syncthreads();  // row 0 (the shift) is read from another thread's slot
     // ---- sweep 1 (shared): shifted sums  sum(x - s), sum((x - s)^2)  with s = the group's first row.  One pass
@@ -145,24 +154,23 @@ __global__ void __launch_bounds__(THREADS)
     for (int j = 0; j < V; ++j) shift[j] = 0.f;
     if (active) {
       Vec<T>::unpack(cache[cq], shift);  // row 0 lives in slot 0 of the thread with row lane 0
-      for (int k = 0; k < K; ++k) {
-        if (rl + k * LANES < rows) {
-          float v[V];
-          Vec<T>::unpack(cache[k * THREADS + threadIdx.x], v);
+      const uint4* slot = cache + threadIdx.x;
+      bn_for_rows(kf, tail, [&]() {
+        float v[V];
+        Vec<T>::unpack(*slot, v);
+        slot += THREADS;
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            const float d = v[j] - shift[j];
-            acc[j] += d;
-            acc[V + j] = fmaf(d, d, acc[V + j]);
-          }
+        for (int j = 0; j < V; ++j) {
+          const float d = v[j] - shift[j];
+          acc[j] += d;
+          acc[V + j] = fmaf(d, d, acc[V + j]);
         }
-      }
+      
+      });
     }
     rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
-    float sc[V], sh[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) sc[j] = sh[j] = 0.f;
     if (active) {
+      float sc[V], sh[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const float md = acc[j] * inv_n;  // mean - shift
@@ -177,159 +185,174 @@ __global__ void __launch_bounds__(THREADS)
           save_rstd[(size_t)g * c + c0 + j] = rstd;
         }
       }
-    }
-    // ---- sweep 2 (shared -> global): normalise (+residual) (+ReLU); refill the cache with the next tile ----
-    T* op = out + row_base * out_stride + c0;
-    const T* rp = (res && active) ? res + row_base * res_stride + c0 : nullptr;
-    for (int k0 = 0; k0 < K; k0 += U) {
-      uint4 rres[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = rl + (k0 + u) * LANES;
-        rres[u] = (rp && r < rows) ? ld16(rp + (size_t)r * res_stride) : zero4;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = rl + (k0 + u) * LANES;
-        if (r < rows) {
-          uint4* slot = &cache[(k0 + u) * THREADS + threadIdx.x];
-          const uint4 raw = *slot;
-          if (xnext) cp_async16(slot, xnext + (size_t)r * x_stride);
-          if (active) {
-            float v[V];
-            Vec<T>::unpack(raw, v);
-#pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-            if (rp) {
-              float e[V];
-              Vec<T>::unpack(rres[u], e);
-#pragma unroll
-              for (int j = 0; j < V; ++j) v[j] += e[j];
-            }
-            if (relu) {
-#pragma unroll
-              for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            st16(op + (size_t)r * out_stride, Vec<T>::pack(v));
-          }
+      // ---- sweep 2 (shared -> global): normalise (+residual) (+ReLU); refill the cache with the next tile ----
+      const size_t row0 = (size_t)g * rows + rl;
+      T* op = out + row0 * out_stride + c0;
+      const T* rp = HAS_RES ? res + row0 * res_stride + c0 : nullptr;
+      uint4* slot = cache + threadIdx.x;
+      auto row = [&](const uint4& rr) {
+        const uint4 raw = *slot;
+        if (xn) {
+          cp_async16(slot, xn);
+          xn += x_step;
         }
+        float v[V];
+        Vec<T>::unpack(raw, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (HAS_RES) {
+          float e[V];
+          Vec<T>::unpack(rr, e);
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] += e[j];
+        }
+        if (RELU) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        st16(op, Vec<T>::pack(v));
+        op += o_step;
+        slot += THREADS;
+      };
+      if (HAS_RES) {
+        // the residual is the only global read of this sweep: keep three rows of it in flight
+        int k = 0;
+        for (; k + 3 <= kf; k += 3) {
+          uint4 rr[3];
+#pragma unroll
+          for (int u = 0; u < 3; ++u) rr[u] = ld16(rp + u * r_step);
+          rp += 3 * r_step;
+#pragma unroll
+          for (int u = 0; u < 3; ++u) row(rr[u]);
+        }
+        for (; k < kf; ++k) {
+          const uint4 rr = ld16(rp);
+          rp += r_step;
+          row(rr);
+        }
+        if (tail) row(ld16(rp));
+      } else {
+        const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+        bn_for_rows(kf, tail, [&]() { row(none); });
       }
+    } else if (xn) {
+      // a thread past the last channel of THIS tile may own channels of the next one: refill only
+      uint4* slot = cache + threadIdx.x;
+      bn_for_rows(kf, tail, [&]() { cp_async16(slot, xn); slot += THREADS; xn += x_step; });
     }
   }
 }
 
 // NT = number of cached tensors: 2 (gradient, x) or 3 (+ the ReLU mask source of relu_mode 2)
-template <typename T, int VPR, int THREADS>
+template <typename T, int VPR, int THREADS, int RELU_MODE>
 __global__ void __launch_bounds__(THREADS)
     gbn_bwd_cached_kernel(const T* dout, const T* x, const T* mask_src, const float* __restrict__ gamma,
                           const float* __restrict__ beta, const float* __restrict__ save_mean,
                           const float* __restrict__ save_rstd, T* dx, int accumulate_dx, T* dres,
                           float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int n_groups, int rows, int c,
-                          int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode) {
-  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V, U = BN_UNROLL;
+                          int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride) {
+  constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V;
+  constexpr bool USE_MASK = RELU_MODE == 2;
   extern __shared__ uint4 cache[];  // [NT][K][THREADS]: gradient (masked in place by sweep 1), x, [mask source]
   __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
   const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
   const float inv_n = 1.f / (float)rows;
-  const int K = (rows + LANES - 1) / LANES;
+  const int kf = rows / LANES;
+  const bool tail = rl < rows - kf * LANES;
+  const int K = kf + (rows - kf * LANES > 0 ? 1 : 0);
   const int n_ct = (c + CT - 1) / CT;
   const int n_tiles = n_ct * n_groups;
-  uint4* cache_g = cache;
-  uint4* cache_x = cache + (size_t)K * THREADS;
-  uint4* cache_m = cache + (size_t)2 * K * THREADS;
-  const bool use_mask = relu_mode == 2;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  const size_t plane = (size_t)K * THREADS;  // uint4 slots per cached tensor
+  const size_t g_step = (size_t)LANES * dout_stride, x_step = (size_t)LANES * x_stride, m_step = (size_t)LANES * mask_stride;
   auto tile_c0 = [&](int tile) { return (tile % n_ct) * CT + cq * V; };
-  // per-tile base pointers of this thread's channel vector (row 0 of the group), computed ONCE per tile: the row loops
-  // below only add r * stride (the tile -> (group, channel tile) division must not sit in the per-row path)
+  // per-tile pointers to this thread's first row, computed ONCE per tile (the tile -> (group, channel tile) division
+  // must not sit in the per-row path)
   struct TilePtrs {
     const T* g;
     const T* x;
     const T* m;
   };
   auto tile_ptrs = [&](int tile) {
-    const size_t row0 = (size_t)(tile / n_ct) * rows;
+    const size_t row0 = (size_t)(tile / n_ct) * rows + rl;
     const int c0 = tile_c0(tile);
     TilePtrs tp;
     tp.g = dout + row0 * dout_stride + c0;
     tp.x = x + row0 * x_stride + c0;
-    tp.m = use_mask ? mask_src + row0 * mask_stride + c0 : nullptr;
+    tp.m = USE_MASK ? mask_src + row0 * mask_stride + c0 : nullptr;
     return tp;
   };
-  auto issue_row = [&](const TilePtrs& tp, int k, int r) {
-    const int slot = k * THREADS + threadIdx.x;
-    cp_async16(&cache_g[slot], tp.g + (size_t)r * dout_stride);
-    cp_async16(&cache_x[slot], tp.x + (size_t)r * x_stride);
-    if (use_mask) cp_async16(&cache_m[slot], tp.m + (size_t)r * mask_stride);
+  auto issue_rows = [&](TilePtrs tp) {  // the whole tile of this thread
+    uint4* slot = cache + threadIdx.x;
+    bn_for_rows(kf, tail, [&]() {
+      cp_async16(slot, tp.g);
+      cp_async16(slot + plane, tp.x);
+      if (USE_MASK) cp_async16(slot + 2 * plane, tp.m);
+      slot += THREADS;
+      tp.g += g_step;
+      tp.x += x_step;
+      if (USE_MASK) tp.m += m_step;
+    
+      });
   };
   int tile = blockIdx.x;
-  if (tile < n_tiles && tile_c0(tile) < c) {
-    const TilePtrs tp = tile_ptrs(tile);
-    for (int k = 0; k < K; ++k) {
-      const int r = rl + k * LANES;
-      if (r < rows) issue_row(tp, k, r);
-    }
-  }
+  if (tile < n_tiles && tile_c0(tile) < c) issue_rows(tile_ptrs(tile));
   for (; tile < n_tiles; tile += gridDim.x) {
     const int g = tile / n_ct, c0 = tile_c0(tile);
     const bool active = c0 < c;
-    const size_t row_base = (size_t)g * rows;
     const int next = tile + gridDim.x;
     const bool refill = next < n_tiles && tile_c0(next) < c;
-    const TilePtrs tp_next = refill ? tile_ptrs(next) : TilePtrs{nullptr, nullptr, nullptr};
-    float mean[V], rstd[V], sc[V], sh[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      mean[j] = active ? save_mean[(size_t)g * c + c0 + j] : 0.f;
-      rstd[j] = active ? save_rstd[(size_t)g * c + c0 + j] : 0.f;
-      const float gm = active ? gamma[c0 + j] : 0.f, bt = active ? beta[c0 + j] : 0.f;
-      sc[j] = rstd[j] * gm;          // same arithmetic as the forward: y = fmaf(x, sc, sh)
-      sh[j] = bt - mean[j] * sc[j];
-    }
+    TilePtrs tn = refill ? tile_ptrs(next) : TilePtrs{nullptr, nullptr, nullptr};
     cp_async_wait_all();  // every thread only reads the slots it filled itself: no barrier needed
-
-    // ---- sweep 1 (shared): mask the gradient in place, accumulate sum g and sum g*(x - mean) ----
     float acc[2 * V];
 #pragma unroll
     for (int j = 0; j < 2 * V; ++j) acc[j] = 0.f;
-    T* drp = (dres && active) ? dres + row_base * dres_stride + c0 : nullptr;
+    float mean[V], rstd[V], sc[V], sh[V];
+    const size_t row0 = (size_t)g * rows + rl;
     if (active) {
-      for (int k = 0; k < K; ++k) {
-        const int r = rl + k * LANES;
-        if (r < rows) {
-          float gv[V], xv[V];
-          Vec<T>::unpack(cache_g[k * THREADS + threadIdx.x], gv);
-          Vec<T>::unpack(cache_x[k * THREADS + threadIdx.x], xv);
-          if (relu_mode == 1) {
 #pragma unroll
-            for (int j = 0; j < V; ++j)
-              if (!(fmaf(xv[j], sc[j], sh[j]) > 0.f)) gv[j] = 0.f;
-          } else if (relu_mode == 2) {
-            float m[V];
-            Vec<T>::unpack(cache_m[k * THREADS + threadIdx.x], m);
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-              if (!(m[j] > 0.f)) gv[j] = 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < V; ++j) {
-            acc[j] += gv[j];
-            acc[V + j] = fmaf(gv[j], xv[j] - mean[j], acc[V + j]);  // x rstd after the reduction
-          }
-          if (relu_mode != 0) {
-            const uint4 pg = Vec<T>::pack(gv);  // exact: masking keeps or zeroes a value that already is a T
-            cache_g[k * THREADS + threadIdx.x] = pg;
-            if (drp) st16(drp + (size_t)r * dres_stride, pg);
-          } else if (drp) {
-            st16(drp + (size_t)r * dres_stride, cache_g[k * THREADS + threadIdx.x]);
-          }
-        }
+      for (int j = 0; j < V; ++j) {
+        mean[j] = save_mean[(size_t)g * c + c0 + j];
+        rstd[j] = save_rstd[(size_t)g * c + c0 + j];
+        sc[j] = rstd[j] * gamma[c0 + j];          // same arithmetic as the forward: y = fmaf(x, sc, sh)
+        sh[j] = beta[c0 + j] - mean[j] * sc[j];
       }
+      // ---- sweep 1 (shared): mask the gradient in place, accumulate sum g and sum g*(x - mean) ----
+      T* drp = dres ? dres + row0 * dres_stride + c0 : nullptr;
+      const size_t d_step = (size_t)LANES * dres_stride;
+      uint4* slot = cache + threadIdx.x;
+      bn_for_rows(kf, tail, [&]() {
+        float gv[V], xv[V];
+        Vec<T>::unpack(*slot, gv);
+        Vec<T>::unpack(*(slot + plane), xv);
+        if (RELU_MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            if (!(fmaf(xv[j], sc[j], sh[j]) > 0.f)) gv[j] = 0.f;
+        } else if (RELU_MODE == 2) {
+          float m[V];
+          Vec<T>::unpack(*(slot + 2 * plane), m);
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            if (!(m[j] > 0.f)) gv[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          acc[j] += gv[j];
+          acc[V + j] = fmaf(gv[j], xv[j] - mean[j], acc[V + j]);  // x rstd after the reduction
+        }
+        if (RELU_MODE != 0) {
+          const uint4 pg = Vec<T>::pack(gv);  // exact: masking keeps or zeroes a value that already is a T
+          *slot = pg;
+          if (drp) st16(drp, pg);
+        } else if (drp) {
+          st16(drp, *slot);
+        }
+        if (drp) drp += d_step;
+        slot += THREADS;
+      
+      });
     }
     rowlane_reduce<2 * V, VPR, THREADS>(acc, red);
-    float kb[V], kc[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) kb[j] = kc[j] = 0.f;
     if (active) {
 #pragma unroll
       for (int j = 0; j < V; ++j) acc[V + j] *= rstd[j];
@@ -341,44 +364,47 @@ __global__ void __launch_bounds__(THREADS)
         }
       }
       // dx = sc*(g - m1 - xhat*m2) = sc*g + kb*x + kc
+      float kb[V], kc[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const float m1 = acc[j] * inv_n, m2 = acc[V + j] * inv_n;
         kb[j] = -sc[j] * m2 * rstd[j];
         kc[j] = -sc[j] * m1 - kb[j] * mean[j];
       }
-    }
-    // ---- sweep 2 (shared -> global): dx; refill the cache with the next tile ----
-    T* dxp = dx + row_base * dx_stride + c0;
-    for (int k0 = 0; k0 < K; k0 += U) {
-      uint4 ro[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = rl + (k0 + u) * LANES;
-        ro[u] = (accumulate_dx && active && r < rows) ? ld16(dxp + (size_t)r * dx_stride) : zero4;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int k = k0 + u, r = rl + k * LANES;
-        if (r < rows) {
-          const uint4 rg = cache_g[k * THREADS + threadIdx.x], rx = cache_x[k * THREADS + threadIdx.x];
-          if (refill) issue_row(tp_next, k, r);
-          if (active) {
-            float gv[V], xv[V], o[V];
-            Vec<T>::unpack(rg, gv);
-            Vec<T>::unpack(rx, xv);
-#pragma unroll
-            for (int j = 0; j < V; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(kb[j], xv[j], kc[j]));
-            if (accumulate_dx) {
-              float e[V];
-              Vec<T>::unpack(ro[u], e);
-#pragma unroll
-              for (int j = 0; j < V; ++j) o[j] += e[j];
-            }
-            st16(dxp + (size_t)r * dx_stride, Vec<T>::pack(o));
-          }
+      // ---- sweep 2 (shared -> global): dx; refill the cache with the next tile ----
+      T* dxp = dx + row0 * dx_stride + c0;
+      const size_t dx_step = (size_t)LANES * dx_stride;
+      uint4* slot = cache + threadIdx.x;
+      bn_for_rows(kf, tail, [&]() {
+        uint4 ro;
+        if (accumulate_dx) ro = ld16(dxp);
+        const uint4 rg = *slot, rx = *(slot + plane);
+        if (refill) {
+          cp_async16(slot, tn.g);
+          cp_async16(slot + plane, tn.x);
+          if (USE_MASK) cp_async16(slot + 2 * plane, tn.m);
+          tn.g += g_step;
+          tn.x += x_step;
+          if (USE_MASK) tn.m += m_step;
         }
-      }
+        float gv[V], xv[V], o[V];
+        Vec<T>::unpack(rg, gv);
+        Vec<T>::unpack(rx, xv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = fmaf(sc[j], gv[j], fmaf(kb[j], xv[j], kc[j]));
+        if (accumulate_dx) {
+          float e[V];
+          Vec<T>::unpack(ro, e);
+#pragma unroll
+          for (int j = 0; j < V; ++j) o[j] += e[j];
+        }
+        st16(dxp, Vec<T>::pack(o));
+        dxp += dx_step;
+        slot += THREADS;
+      
+      });
+    } else if (refill) {
+      issue_rows(tn);
     }
   }
 }
@@ -763,19 +789,53 @@ static int bn_persistent_grid(size_t smem_dyn, size_t smem_static, int threads, 
   return grid < n_tiles ? grid : n_tiles;
 }
 
+template <typename T, int VPR, int THREADS, bool HAS_RES, bool RELU>
+static int run_fwd_cached_v(const void* x, void* out, const void* res, const float* gamma, const float* beta,
+                            float* save_mean, float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride,
+                            int res_stride, float eps, cudaStream_t st) {
+  static size_t granted = 32 * 1024;
+  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16;
+  int rc = bn_smem_optin(gbn_fwd_cached_kernel<T, VPR, THREADS, HAS_RES, RELU>, smem, &granted);
+  if (rc) return rc;
+  const int n_tiles = ceil_div(c, VPR * Vec<T>::N) * n_groups;
+  const int grid = bn_persistent_grid(smem, (THREADS / 32 + 1) * VPR * 2 * Vec<T>::N * 4, THREADS, n_tiles);
+  gbn_fwd_cached_kernel<T, VPR, THREADS, HAS_RES, RELU><<<grid, THREADS, smem, st>>>(
+      static_cast<const T*>(x), static_cast<T*>(out), static_cast<const T*>(res), gamma, beta, save_mean, save_rstd,
+      n_groups, rows, c, x_stride, out_stride, res_stride, eps);
+  return DARDS_OK;
+}
+
 template <typename T, int VPR, int THREADS>
 static int run_fwd_cached(const void* x, void* out, const void* res, const float* gamma, const float* beta,
                           float* save_mean, float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride,
                           int res_stride, float eps, int relu, cudaStream_t st) {
-  static size_t granted = 32 * 1024;
-  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16;
-  int rc = bn_smem_optin(gbn_fwd_cached_kernel<T, VPR, THREADS>, smem, &granted);
+#define BN_FWD_V(R, A)                                                                                               \
+  return run_fwd_cached_v<T, VPR, THREADS, R, A>(x, out, res, gamma, beta, save_mean, save_rstd, n_groups, rows, c, \
+                                                 x_stride, out_stride, res_stride, eps, st)
+  if (res) {
+    if (relu) BN_FWD_V(true, true);
+    BN_FWD_V(true, false);
+  }
+  if (relu) BN_FWD_V(false, true);
+  BN_FWD_V(false, false);
+#undef BN_FWD_V
+}
+
+template <typename T, int VPR, int THREADS, int RELU_MODE>
+static int run_bwd_cached_v(const void* dout, const void* x, const void* mask_src, const float* gamma, const float* beta,
+                            const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
+                            float* dgamma_part, float* dbeta_part, int n_groups, int rows, int c, int dout_stride,
+                            int x_stride, int mask_stride, int dx_stride, int dres_stride, cudaStream_t st) {
+  static size_t granted = 24 * 1024;
+  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16 * (RELU_MODE == 2 ? 3 : 2);
+  int rc = bn_smem_optin(gbn_bwd_cached_kernel<T, VPR, THREADS, RELU_MODE>, smem, &granted);
   if (rc) return rc;
   const int n_tiles = ceil_div(c, VPR * Vec<T>::N) * n_groups;
   const int grid = bn_persistent_grid(smem, (THREADS / 32 + 1) * VPR * 2 * Vec<T>::N * 4, THREADS, n_tiles);
-  gbn_fwd_cached_kernel<T, VPR, THREADS><<<grid, THREADS, smem, st>>>(
-      static_cast<const T*>(x), static_cast<T*>(out), static_cast<const T*>(res), gamma, beta, save_mean, save_rstd,
-      n_groups, rows, c, x_stride, out_stride, res_stride, eps, relu);
+  gbn_bwd_cached_kernel<T, VPR, THREADS, RELU_MODE><<<grid, THREADS, smem, st>>>(
+      static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,
+      save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, n_groups, rows, c,
+      dout_stride, x_stride, mask_stride, dx_stride, dres_stride);
   return DARDS_OK;
 }
 
@@ -784,17 +844,14 @@ static int run_bwd_cached(const void* dout, const void* x, const void* mask_src,
                           const float* save_mean, const float* save_rstd, void* dx, int accumulate_dx, void* dres,
                           float* dgamma_part, float* dbeta_part, int n_groups, int rows, int c, int dout_stride,
                           int x_stride, int mask_stride, int dx_stride, int dres_stride, int relu_mode, cudaStream_t st) {
-  static size_t granted = 24 * 1024;
-  const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16 * (relu_mode == 2 ? 3 : 2);
-  int rc = bn_smem_optin(gbn_bwd_cached_kernel<T, VPR, THREADS>, smem, &granted);
-  if (rc) return rc;
-  const int n_tiles = ceil_div(c, VPR * Vec<T>::N) * n_groups;
-  const int grid = bn_persistent_grid(smem, (THREADS / 32 + 1) * VPR * 2 * Vec<T>::N * 4, THREADS, n_tiles);
-  gbn_bwd_cached_kernel<T, VPR, THREADS><<<grid, THREADS, smem, st>>>(
-      static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,
-      save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, n_groups, rows, c,
-      dout_stride, x_stride, mask_stride, dx_stride, dres_stride, relu_mode);
-  return DARDS_OK;
+#define BN_BWD_V(M)                                                                                                     \
+  return run_bwd_cached_v<T, VPR, THREADS, M>(dout, x, mask_src, gamma, beta, save_mean, save_rstd, dx, accumulate_dx, \
+                                              dres, dgamma_part, dbeta_part, n_groups, rows, c, dout_stride, x_stride, \
+                                              mask_stride, dx_stride, dres_stride, st)
+  if (relu_mode == 0) BN_BWD_V(0);
+  if (relu_mode == 1) BN_BWD_V(1);
+  BN_BWD_V(2);
+#undef BN_BWD_V
 }
 
 #define BN_DISPATCH_CFG(cfg, CALL)                                   \
