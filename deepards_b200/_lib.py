@@ -5,15 +5,24 @@ error, a RuntimeError is raised.
 """
 import ctypes
 import os
-from ctypes import c_float, c_int, c_longlong, c_ulonglong, c_void_p
+from ctypes import c_double, c_float, c_int, c_longlong, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdeepards_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
-P, I, LL, ULL, F = c_void_p, c_int, c_longlong, c_ulonglong, c_float
+P, I, LL, ULL, F, D = c_void_p, c_int, c_longlong, c_ulonglong, c_float, c_double
+
+
+class GradcamDesc(ctypes.Structure):
+    """dards_gradcam_desc (include/deepards_b200.h)."""
+    _fields_ = [(n, c_void_p) for n in ("a", "w", "bias", "target_dev", "logits", "target_used", "read_raw", "read_u8",
+                                        "seq_raw", "seq_u8", "read_resized", "seq_resized", "conv_out", "grad_out")] + \
+               [(n, c_int) for n in ("a_stride", "target", "n_groups", "group", "l", "f", "n_out", "resized_len", "dtype",
+                                     "reserved")]
+
 
 # name -> argtypes (all functions return int unless listed in _RESTYPES)
 _SIGNATURES = {
@@ -45,6 +54,8 @@ _SIGNATURES = {
     "dards_bce_with_logits": [P, P, P, P, I, F, P],
     "dards_clamp_sgd_nesterov": [P, P, P, LL, F, F, F, F, F, I, P],
     "dards_clamp_adam": [P, P, P, P, LL, F, F, F, F, F, F, I, P],
+    "dards_scale_windows": [P, I, P, LL, D, D, I, P],
+    "dards_gradcam": [ctypes.POINTER(GradcamDesc), P],
     "dards_tc_debug_set": [I, I],
 }
 _RESTYPES = {"dards_last_error": ctypes.c_char_p, "dards_launch_count": c_longlong, "dards_conv1d_wgrad_workspace_bytes": c_longlong}

@@ -63,6 +63,9 @@ int launch_clamp_sgd(float*, const float*, float*, long long, float, float, floa
 int launch_clamp_adam(float*, const float*, float*, float*, long long, float, float, float, float, float, float, int,
                       cudaStream_t);
 
+int launch_gradcam(const dards_gradcam_desc&, cudaStream_t);
+int launch_scale_windows(const void*, int, float*, long long, double, double, int, cudaStream_t);
+
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
 static int conv_out_len(int l_in, int ktaps, int stride, int pad) { return (l_in + 2 * pad - ktaps) / stride + 1; }
@@ -73,7 +76,7 @@ using namespace dards;
 
 extern "C" {
 
-int dards_version(void) { return 3; }
+int dards_version(void) { return 4; }
 
 const char* dards_last_error(void) { return g_err; }
 
@@ -300,6 +303,20 @@ int dards_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp
                      float beta1, float beta2, float eps, float clip, float grad_scale, int step, void* stream) {
   DARDS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n >= 0, "clamp_adam: bad argument");
   return launch_clamp_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, clip, grad_scale, step, S(stream));
+}
+
+int dards_scale_windows(const void* raw, int raw_f64, float* out, long long n, double mu, double std, int padded,
+                        void* stream) {
+  DARDS_CHECK_ARG(n >= 0, "scale_windows: negative size");
+  return launch_scale_windows(raw, raw_f64, out, n, mu, std, padded, S(stream));
+}
+
+int dards_gradcam(const dards_gradcam_desc* d, void* stream) {
+  DARDS_CHECK_ARG(d != nullptr, "gradcam: null descriptor");
+  DARDS_CHECK_ARG(d->n_groups >= 0, "gradcam: negative size");
+  DARDS_CHECK_ARG(d->resized_len >= 0 && ((d->read_resized == nullptr && d->seq_resized == nullptr) || d->resized_len > 0),
+                  "gradcam: resized outputs need resized_len > 0");
+  return launch_gradcam(*d, S(stream));
 }
 
 int dards_tc_debug_set(int key, int value) { return tc_debug_set(key, value); }

@@ -140,8 +140,20 @@ class DataParallelTrainer(object):
     def train_step(self, x, target):
         """x: this rank's (B_local, 20, 1, 224) on the device, target (B_local, 2).  Returns the device tensor
         holding the local mean loss (no host synchronisation)."""
+        return self._train_step(x, target, None)
+
+    def train_step_raw(self, raw, target, mu, std, padded=False):
+        """The same step fed with RAW float64 / float32 windows on the device: the dataset's `(data - mu) / std` +
+        `.float()` (dataset.py:1375-1379) runs as the plan's input load, so the host pipeline only has to hand over
+        the stored windows."""
+        return self._train_step(raw, target, (mu, std, padded))
+
+    def _train_step(self, x, target, scaling):
         plan = self.plan_for(x)
-        plan.load_input(x)
+        if scaling is None:
+            plan.load_input(x)
+        else:
+            plan.load_raw(x, *scaling)
         t_static = plan.__dict__.get("_dp_target")
         if t_static is None:
             t_static = plan._dp_target = torch.empty((plan.logits.numel(),), dtype=torch.float32, device=self.device)

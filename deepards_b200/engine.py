@@ -591,6 +591,18 @@ class Plan(object):
             raise RuntimeError("plan was built for %d breaths of %d samples, got %s" % (self.N, SEQ_LEN, tuple(x.shape)))
         self.x_buf.copy_(x.reshape(self.N, SEQ_LEN), non_blocking=True)
 
+    def load_raw(self, raw, mu, std, padded=False):
+        """The dataset's scaling step fused into the input load (dataset.py:1375-1379, train_ards_detector.py:150-151):
+        raw float64 / float32 windows on the device -> (raw - mu) / std as float32, straight into the static input
+        buffer (float64 arithmetic, one rounding: bit-exact with the reference's numpy + .float())."""
+        if raw.shape[-1] != SEQ_LEN or raw.numel() != self.N * SEQ_LEN:
+            raise RuntimeError("plan was built for %d breaths of %d samples, got %s" % (self.N, SEQ_LEN, tuple(raw.shape)))
+        if raw.device != self.device or raw.dtype not in (torch.float64, torch.float32):
+            raise RuntimeError("raw windows must be float64 / float32 tensors on %s" % (self.device,))
+        raw = raw.contiguous()
+        _lib.call("dards_scale_windows", raw.data_ptr(), 1 if raw.dtype == torch.float64 else 0, self.x_buf.data_ptr(),
+                  raw.numel(), float(mu), float(std), 1 if padded else 0, self._stream())
+
     def run_forward(self):
         st = self._stream()
         self._pack_if_needed(st)

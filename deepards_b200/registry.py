@@ -8,7 +8,8 @@ package with no other change (INTEGRATION.md shows the two-line edit a maintaine
 """
 from .densenet import densenet18, densenet121
 from .resnet import resnet18, resnet34
-from .torch_cnn_linear_network import CNNLinearNetwork, CNNSingleBreathLinearNetwork
+from .torch_cnn_linear_network import (CNNDoubleLinearNetwork, CNNLinearComprToRF, CNNLinearNetwork, CNNLinearToMean,
+                                       CNNRegressor, CNNSingleBreathLinearNetwork)
 
 base_networks = {
     'resnet18': resnet18,
@@ -21,6 +22,10 @@ base_networks = {
 network_heads = {
     'cnn_linear': CNNLinearNetwork,
     'cnn_single_breath_linear': CNNSingleBreathLinearNetwork,
+    'cnn_linear_to_mean': CNNLinearToMean,
+    'cnn_linear_compr_to_rf': CNNLinearComprToRF,
+    'cnn_double_linear': CNNDoubleLinearNetwork,
+    'cnn_regressor': CNNRegressor,
 }
 
 
@@ -29,4 +34,6 @@ def install(train_module):
     train_module.base_networks.update(base_networks)
     train_module.CNNLinearNetwork = CNNLinearNetwork
     train_module.CNNSingleBreathLinearNetwork = CNNSingleBreathLinearNetwork
+    for cls in (CNNLinearToMean, CNNLinearComprToRF, CNNDoubleLinearNetwork, CNNRegressor):
+        setattr(train_module, cls.__name__, cls)
     return train_module

@@ -9,6 +9,7 @@ BatchNorm sees one sequence at a time), this implementation runs ALL B*20 breath
 BatchNorm kernels take their statistics per group of 20 consecutive breaths -- same numbers, one launch
 sequence, no O(B^2) torch.cat.
 """
+import torch
 import torch.nn as nn
 
 from . import autograd as _ag
@@ -29,6 +30,13 @@ class _HeadBase(_Picklable, nn.Module):
             raise NotImplementedError("deepards_b200 heads take (B, breaths, 1, 224) inputs, got %s" % (tuple(x.shape),))
         if not hasattr(self.breath_block, "network_name") or not hasattr(self.breath_block, "precision"):
             raise TypeError("breath_block must be a deepards_b200 backbone (resnet18 / densenet18 from this package)")
+
+    def _sequence_features(self, x):
+        """(B, S, 1, 224) -> pooled backbone features (B, S, F): ONE batched plan with BatchNorm group S, i.e. what the
+        reference's `breath_block(x[i])` loop + torch.cat produces (torch_cnn_linear_network.py:22-24)."""
+        self._check(x)
+        feat = _ag.run_plan(self, self.breath_block, None, x, x.shape[1], "backbone", _drop_key(self.breath_block))
+        return feat.view(x.shape[0], x.shape[1], -1)
 
     @property
     def precision(self):
@@ -67,3 +75,63 @@ class CNNSingleBreathLinearNetwork(_HeadBase):
         self._check(x)
         return _ag.run_plan(self, self.breath_block, self.linear_final, x, x.shape[1], "per_breath",
                             _drop_key(self.breath_block))
+
+
+# ---- sibling heads on the same backbone: the backbone runs as one batched plan, the few-kB head
+# ---- arithmetic behind it stays in torch ------------------------------------------------------------------------
+class CNNLinearToMean(_HeadBase):
+    """Linear(F, 2) on the mean of the sequence's breath features (torch_cnn_linear_network.py:7-25)."""
+
+    def __init__(self, breath_block):
+        super(CNNLinearToMean, self).__init__()
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.linear_final = nn.Linear(self.breath_block.n_out_filters, 2)
+
+    def forward(self, x, metadata=None):
+        return self.linear_final(torch.mean(self._sequence_features(x), dim=1))
+
+
+class CNNLinearComprToRF(_HeadBase):
+    """Linear(F, 2) on the per-feature median over the sequence (torch_cnn_linear_network.py:28-46)."""
+
+    def __init__(self, breath_block):
+        super(CNNLinearComprToRF, self).__init__()
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.linear_final = nn.Linear(self.breath_block.n_out_filters, 2)
+
+    def forward(self, x, metadata=None):
+        return self.linear_final(torch.median(self._sequence_features(x), dim=1)[0])
+
+
+class CNNDoubleLinearNetwork(_HeadBase):
+    """Linear(F, 2) per breath, then Linear(2 * S, 2) per sequence (torch_cnn_linear_network.py:70-89)."""
+
+    def __init__(self, breath_block, sequence_size, metadata_features):
+        super(CNNDoubleLinearNetwork, self).__init__()
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.linear_intermediate = nn.Linear(self.breath_block.n_out_filters, 2)
+        self.linear_final = nn.Linear(2 * sequence_size + metadata_features, 2)
+
+    def forward(self, x, metadata=None):
+        feat = self._sequence_features(x)
+        return self.linear_final(self.linear_intermediate(feat).reshape(x.shape[0], -1))
+
+
+class CNNRegressor(_HeadBase):
+    """Linear(F, n_final_features) on a FLAT batch of breaths: BatchNorm group = the whole batch
+    (torch_cnn_bm_regressor.py:6-19).  x: (N, 1, 224)."""
+
+    def __init__(self, breath_block, n_final_features):
+        super(CNNRegressor, self).__init__()
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.linear_final = nn.Linear(breath_block.n_out_filters, n_final_features)
+
+    def forward(self, x, metadata=None):
+        # input should be in shape: (batches, chans, 224)
+        if x.shape[-1] != 224:
+            raise Exception('input breaths must have sequence length of 224')
+        return self.linear_final(self.breath_block(x).squeeze())

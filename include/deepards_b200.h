@@ -204,6 +204,48 @@ int dards_clamp_sgd_nesterov(float* param, const float* grad, float* momentum_bu
 int dards_clamp_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                      float beta1, float beta2, float eps, float clip, float grad_scale, int step, void* stream);
 
+/* ---- input contract ------------------------------------------------------------------- */
+/* ARDSRawDataset.__getitem__ scaling + the trainer's .float() (dataset.py:1375-1379, train_ards_detector.py:150-151):
+ * out[i] = (float)((raw[i] - mu) / std), float64 arithmetic, one rounding -- bit-exact with numpy.  `raw` is a DEVICE
+ * array of n float64 (raw_f64 != 0) or float32 samples.  padded != 0 is the padded_breath_by_breath rule
+ * (_get_padding_mask, dataset.py:1406-1409): mu is subtracted only where raw[i] != 0, so zero padding stays zero. */
+int dards_scale_windows(const void* raw, int raw_f64, float* out, long long n, double mu, double std, int padded,
+                        void* stream);
+
+/* ---- GradCAM maps ---------------------------------------------------------------------- */
+/* gradcam.py:40-65, 83-107 (forward through ReLU/AvgPool/Linear + one-hot backward to the norm5 output A) and the
+ * numpy reductions of MaxMinNormCam / UnNormalizedCam (gradcam.py:125-162, 195-205), one CTA per sequence.
+ * dA is taken in closed form, dA[n,c,l] = (A[n,c,l] > 0) ? W[target][n*F+c] / L : 0, so no convolution backward runs.
+ *   a            (n_groups*group, L, F) channels-last feature map in `dtype`, row stride a_stride (L <= 8)
+ *   w, bias      linear_final of CNNLinearNetwork: (n_out, group*F), (n_out)
+ *   target_dev   per-sequence class index on the DEVICE (nullable); else `target` for every sequence;
+ *                a value < 0 means "the predicted class" (np.argmax of the logits, gradcam.py:101-102)
+ * outputs (every pointer except logits may be NULL):
+ *   logits (n_groups, n_out); target_used (n_groups)
+ *   read_raw / read_u8   (n_groups*group, L): generate_read_cam before / after normalize()
+ *   seq_raw / seq_u8     (n_groups, L):       generate_cam before / after normalize() (max(seq_raw,0) = UnNormalizedCam)
+ *   read_resized / seq_resized  (.., resized_len) uint8: cv2.resize(cam, (1, resized_len)) (patient_gradcam.py:217, 229)
+ *   conv_out / grad_out  (n_groups*group, F, L) fp32: A and dA in the reference's layout
+ *                        (generate_one_hot_grad_and_output, gradcam.py:83-99) */
+typedef struct dards_gradcam_desc {
+  const void* a;
+  const float* w;
+  const float* bias;
+  const int* target_dev;
+  float* logits;
+  int* target_used;
+  float* read_raw;
+  uint8_t* read_u8;
+  float* seq_raw;
+  uint8_t* seq_u8;
+  uint8_t* read_resized;
+  uint8_t* seq_resized;
+  float* conv_out;
+  float* grad_out;
+  int a_stride, target, n_groups, group, l, f, n_out, resized_len, dtype, reserved;
+} dards_gradcam_desc;
+int dards_gradcam(const dards_gradcam_desc* desc /* HOST struct, read during the call */, void* stream);
+
 /* ---- debugging ----------------------------------------------------------------------- */
 /* Overrides one field of the tcgen05 shared-memory / instruction descriptors (key: 0 = LBO field,
  * 1 = version field, 2 = SBO field for K-major tiles; 4 = epilogue (0 direct stores, 1 TMA store); 5 = 0 | 1 forces

@@ -31,6 +31,8 @@ Reference call sites restated here
   * BCEWithLogits loss .................... deepards/train_ards_detector.py:530, 929-930
   * gradient clamp hook ................... deepards/train_ards_detector.py:474-476
   * GradCAM forward/backward .............. deepards/gradcam.py:40-65, 83-107
+  * GradCAM maps (read / sequence) ........ deepards/gradcam.py:125-162, 195-205
+  * window scaling (input contract) ....... deepards/dataset.py:1375-1379, 1406-1409
 """
 from __future__ import annotations
 
@@ -300,23 +302,46 @@ def backbone_forward(sd, x, prefix: str = "breath_block.", **kw):
     return resnet_forward(sd, x, prefix, **kw)
 
 
-def cnn_linear_forward(sd, x, per_breath: bool = False, **kw):
+def cnn_linear_forward(sd, x, per_breath: bool = False, head: Optional[str] = None, **kw):
     """The reference's per-sequence loop (torch_cnn_linear_network.py:104-113): each
     x[i] of shape (20, C, 224) is one BatchNorm sub-batch.  Returns (B, 2), or
-    (B, 20, 2) for the per-breath head (torch_cnn_linear_network.py:57-67)."""
+    (B, 20, 2) for the per-breath head (torch_cnn_linear_network.py:57-67).
+    head: None / 'cnn_linear' / 'per_breath', or a sibling head on the same loop --
+    'to_mean' (:7-25), 'compr_to_rf' (:28-46), 'double_linear' (:70-89)."""
     if x.shape[-1] != SEQ_LEN:
         raise Exception("input breaths must have sequence length of 224")
+    head = head or ("per_breath" if per_breath else "cnn_linear")
     w, b = sd["linear_final.weight"], sd["linear_final.bias"]
     rows = []
     for i in range(x.shape[0]):
         if kw.get("hooks") is not None:
             kw["hooks"].seq = i
         feat = backbone_forward(sd, x[i], **kw)
-        if per_breath:
+        if head == "per_breath":
             rows.append(F.linear(feat, w, b).unsqueeze(0))
-        else:
+        elif head == "cnn_linear":
             rows.append(F.linear(feat.reshape(-1), w, b).unsqueeze(0))
-    return torch.cat(rows, 0)
+        elif head == "double_linear":
+            mid = F.linear(feat, sd["linear_intermediate.weight"], sd["linear_intermediate.bias"])
+            rows.append(F.linear(mid.reshape(-1).unsqueeze(0), w, b))
+        elif head in ("to_mean", "compr_to_rf"):
+            rows.append(feat.unsqueeze(0))
+        else:
+            raise ValueError(head)
+    out = torch.cat(rows, 0)
+    if head == "to_mean":
+        return F.linear(torch.mean(out, dim=1), w, b)
+    if head == "compr_to_rf":
+        return F.linear(torch.median(out, dim=1)[0], w, b)
+    return out
+
+
+def regressor_forward(sd, x, **kw):
+    """CNNRegressor.forward, torch_cnn_bm_regressor.py:14-19: the backbone on a FLAT batch x:(N, 1, 224)
+    (BatchNorm over all N breaths), then Linear."""
+    if x.shape[-1] != SEQ_LEN:
+        raise Exception("input breaths must have sequence length of 224")
+    return F.linear(backbone_forward(sd, x, **kw).squeeze(), sd["linear_final.weight"], sd["linear_final.bias"])
 
 
 def bce_with_logits(outputs, target):
@@ -361,6 +386,84 @@ def gradcam_forward_backward(sd, x, target: Optional[int] = None):
         target = int(out.argmax())
     (da,) = torch.autograd.grad(out[0, target], a)
     return a.detach(), da, out.detach()
+
+
+def cam_normalize(cam):
+    """MaxMinNormCam.normalize, gradcam.py:156-161: ReLU, min-max to [0,1], truncate to uint8.
+    numpy float32 arithmetic like the reference (cam arrays are float32 there)."""
+    import numpy as np
+    cam = np.maximum(np.asarray(cam, dtype=np.float32), 0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cam = (cam - np.min(cam)) / (np.max(cam) - np.min(cam))
+        return np.uint8(cam * 255)
+
+
+def gradcam_read_cam(sd, x, target: Optional[int] = None):
+    """MaxMinNormCam.generate_read_cam, gradcam.py:125-136: one CAM row per breath of the sequence.
+    Returns (cam uint8 (20,7), raw float32 cam (20,7) before normalisation, model output (1,2))."""
+    import numpy as np
+    a, da, out = gradcam_forward_backward(sd, x, target)
+    conv_output, grad = a.numpy(), da.numpy()
+    weights = np.mean(grad, axis=(2,))
+    raw = np.zeros((conv_output.shape[0], conv_output.shape[2]), dtype=np.float32)
+    for i in range(conv_output.shape[0]):
+        for j in range(conv_output.shape[1]):
+            raw[i] += weights[i, j] * conv_output[i, j, :]
+    cam = np.stack([cam_normalize(raw[i]) for i in range(raw.shape[0])])
+    return cam, raw, out
+
+
+def gradcam_seq_cam(sd, x, target: Optional[int] = None, normalize: bool = True):
+    """MaxMinNormCam.generate_cam (gradcam.py:138-154) / UnNormalizedCam.generate_cam (:195-205): ONE CAM row for
+    the whole sequence (channel weights and activations averaged over the breaths).  Returns (cam, raw, out)."""
+    import numpy as np
+    a, da, out = gradcam_forward_backward(sd, x, target)
+    conv_output, grad = a.numpy(), da.numpy()
+    weights = np.mean(grad, axis=(0, 2))
+    conv_output = np.mean(conv_output, axis=0)
+    raw = np.zeros(conv_output.shape[1:], dtype=np.float32)
+    for i, w in enumerate(weights):
+        raw += w * conv_output[i, :]
+    return (cam_normalize(raw) if normalize else raw), raw, out
+
+
+def cam_resize_linear_u8(cam, out_len: int = SEQ_LEN):
+    """cv2.resize(cam, (1, out_len)) of a uint8 column (patient_gradcam.py:217, 227-229), i.e. OpenCV's default
+    INTER_LINEAR for 8-bit images: half-pixel centres, coefficients quantised to 11 bits, the vertical pass computing
+    ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2 on rows pre-scaled by 2^11.
+    PARITY UNPINNED: OpenCV (opencv-python, an un-vendored third-party dependency, environment-py3.yml) is absent
+    from this image, so this restates the published algorithm (modules/imgproc/src/resize.cpp, 4.x) without a vector
+    from the library itself."""
+    import numpy as np
+    cam = np.asarray(cam, dtype=np.uint8).ravel()
+    n = cam.shape[0]
+    scale = n / float(out_len)
+    out = np.zeros(out_len, dtype=np.uint8)
+    for d in range(out_len):
+        fy = (d + 0.5) * scale - 0.5
+        sy = int(math.floor(fy))
+        fy -= sy
+        y0, y1 = min(max(sy, 0), n - 1), min(max(sy + 1, 0), n - 1)
+        b0 = int(np.rint(np.float32((1.0 - fy) * 2048)))
+        b1 = int(np.rint(np.float32(fy * 2048)))
+        s0, s1 = int(cam[y0]) * 2048, int(cam[y1]) * 2048
+        out[d] = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2
+    return out
+
+
+def scale_windows(data, mu: float, std: float, padded: bool = False):
+    """ARDSRawDataset.__getitem__ scaling, dataset.py:1375-1379 (+ `_get_padding_mask`, :1406-1409) followed by the
+    trainer's `.float()` (train_ards_detector.py:150-151): float64 arithmetic, one rounding to float32.
+    padded=True is the padded_breath_by_breath rule: mu is subtracted only where the raw sample is non-zero."""
+    import numpy as np
+    data = np.asarray(data, dtype=np.float64)
+    if padded:
+        mask = np.zeros(data.shape)
+        np.put(mask, np.where(data.ravel() != 0)[0], v=mu)
+        data = (data - mask) / std
+    else:
+        data = (data - mu) / std
+    return torch.from_numpy(data).float()
 
 
 # --------------------------------------------------------------------------
