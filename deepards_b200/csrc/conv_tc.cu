@@ -24,7 +24,7 @@
 
 namespace dards {
 
-int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1;
+int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1;
 
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
@@ -782,6 +782,7 @@ int tc_debug_set(int key, int value) {
   else if (key == 4) g_dbg_epilogue = value;
   else if (key == 5) g_dbg_conv3 = value;
   else if (key == 6) g_dbg_stages = value;
+  else if (key == 7) g_dbg_wgrad_fuse = value;
   else {
     set_error("tc_debug_set: unknown key %d", key);
     return DARDS_ERR_INVALID_ARGUMENT;

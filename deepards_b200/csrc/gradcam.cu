@@ -227,9 +227,9 @@ __global__ void scale_windows_kernel(const R* __restrict__ raw, float* __restric
 
 int launch_scale_windows(const void* raw, int raw_f64, float* out, long long n, double mu, double std, int padded,
                          cudaStream_t st) {
-  DARDS_CHECK_ARG(raw && out, "scale_windows: null pointer");
   DARDS_CHECK_ARG(std != 0.0, "scale_windows: std must not be 0");
   if (n == 0) return DARDS_OK;
+  DARDS_CHECK_ARG(raw && out, "scale_windows: null pointer");
   long long b = (n + 255) / 256;
   if (b > 148LL * 8) b = 148LL * 8;
   if (raw_f64)

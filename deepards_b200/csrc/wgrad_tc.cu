@@ -7,12 +7,18 @@
 // reduction index, which is exactly the canonical SWIZZLE_128B MN-major UMMA layout (8-row groups 1024 B apart =
 // SBO, 64-channel chunks LBO apart).  No transposition anywhere.
 //
-// One TMA load per operand serves all taps: each breath is staged with a zero halo row on both sides
-// ([0, dout[0..L-1], 0] and the input shifted by two rows), the halo coming for free from the TMA
-// out-of-bounds fill.  Tap t then multiplies the SAME staged input tile, read through a descriptor whose start
-// address is advanced by t rows (t * 128 B); where the shifted rows run into the neighbouring breath they meet a
-// zero halo row of dout, so nothing leaks across breaths.  Stride-2 convolutions stage the two parity planes of
-// the input (4-D view (C, 2, L/2, N)) as two tiles.
+// One TMA load per operand serves all taps: each breath is staged with ONE zero halo row -- dout as
+// [dout[0..L-1], 0], the input as [0, in[0..L-1]] -- the halo coming for free from the TMA out-of-bounds fill.
+// Tap t then multiplies the SAME staged input tile, read through a descriptor whose start address is advanced by
+// t rows (t * 128 B): dout row j meets staged input row j + t = in[j + t - 1].  Where the shifted rows run into the
+// next breath they meet either its leading zero row (the conv padding) or this breath's zero dout row, so nothing
+// leaks across breaths.  Stride-2 convolutions stage the two parity planes of the input (4-D view (C, 2, L/2, N))
+// as two tiles.
+//
+// 64 input channels, 3 taps, stride 1: the three taps are ONE MMA with N = 192.  For an MN-major operand the
+// descriptor's leading-byte-offset is the distance between consecutive 64-column chunks; LBO = 128 B (one row) makes
+// chunk t the tile shifted by t rows, i.e. tap t, so D[co, t*64 + ci] comes out of a single instruction that reads
+// the dout tile once instead of three times.
 //
 // Tile: 128 output channels (TMEM lanes) x up to 128 input channels (columns) x up to 3 taps (3 accumulators =
 // 384 TMEM columns).  Split-K over groups of breaths; every CTA writes its fp32 partial tile and a second kernel
@@ -47,6 +53,8 @@ struct WgTcParams {
   int stages, stage_bytes;
   int a_bytes, b_bytes;        // bytes of the dout tile / of one input tile inside a stage (1 or 2 64-channel chunks)
   int base_offset_mode;        // 1 (default): base_offset 0;  0: (start >> 7) & 7 -- kept for the probe only
+  int fuse_taps;               // 1: the 3 taps are the 3 column chunks of one N = 192 MMA (c_in == 64, stride 1)
+  int tap_cols;                // TMEM column distance between the taps' accumulators (128, or 64 when fused)
 };
 
 __global__ void __launch_bounds__(WG_TC_THREADS, 1)
@@ -144,6 +152,9 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
         d_tmem[t] = tmem_base + (uint32_t)t * 128u;
       }
       const int n_taps = p.n_taps;
+      // fused taps: N = 192, chunk stride (LBO) = one 128-byte row
+      const uint32_t idesc_f = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(192 >> 3) << 17);
+      const uint64_t bf_tmpl = make_sw128_desc(0, 128 >> 4, 1024 >> 4, 1, 0) + (uint64_t)(p.a_bytes >> 4);
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -151,7 +162,15 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
         uint64_t a_desc = a_tmpl + sa16;
         uint64_t b0 = b_tmpl[0] + sa16, b1 = b_tmpl[1] + sa16, b2 = b_tmpl[2] + sa16;
         uint32_t acc = it != 0 ? 1u : 0u;
-        if (n_taps == 3) {
+        if (p.fuse_taps) {
+          uint64_t bf = bf_tmpl + sa16;
+#pragma unroll 2
+          for (int kk = 0; kk < k_steps; ++kk) {
+            umma_bf16(d_tmem[0], a_desc, bf, idesc_f, acc);
+            a_desc += 128; bf += 128;
+            acc = 1u;
+          }
+        } else if (n_taps == 3) {
 #pragma unroll 2
           for (int kk = 0; kk < k_steps; ++kk) {
             umma_bf16(d_tmem[0], a_desc, b0, idesc, acc);
@@ -190,7 +209,7 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       for (int c0 = 0; c0 < ci_n; c0 += 16) {
         uint32_t v[16];
         if (n_iters > 0) {
-          tmem_ld16(t_row + (uint32_t)t * 128u + (uint32_t)c0, v);
+          tmem_ld16(t_row + (uint32_t)(t * p.tap_cols) + (uint32_t)c0, v);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -260,13 +279,13 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   if (stride != 1 && stride != 2) return w;
   if (c_in % 16 || c_out % 8 || l_in != l_out * stride) return w;
   const int halo = ktaps == 3 ? 1 : 0;
-  p.p_rows = l_out + 2 * halo;
-  p.a_start = -halo;
+  p.p_rows = l_out + halo;     // dout rows [0, L] (row L = zero fill), input rows [-1, L-1] (row -1 = zero fill)
+  p.a_start = 0;
   p.n_taps = ktaps;
   if (stride == 1) {
     p.n_btiles = 1;
     p.b_plane[0] = 0;
-    p.b_start[0] = -2 * halo;  // staged row i = in[i - 2]; tap t of dout row j pairs with staged row j + t
+    p.b_start[0] = -halo;  // staged row i = in[i - 1]; tap t of dout row j pairs with staged row j + t
     for (int t = 0; t < ktaps; ++t) {
       p.tap_btile[t] = 0;
       p.tap_shift[t] = t;
@@ -274,8 +293,8 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   } else if (ktaps == 3) {
     // in[2q + t - 1]: t = 1 -> plane 0 row q; t = 0 -> plane 1 row q-1; t = 2 -> plane 1 row q
     p.n_btiles = 2;
-    p.b_plane[0] = 0; p.b_start[0] = -1;  // staged row i = plane0[i - 1]: dout row j=q+1 pairs with row j
-    p.b_plane[1] = 1; p.b_start[1] = -2;  // staged row i = plane1[i - 2]: tap 0 -> row j, tap 2 -> row j + 1
+    p.b_plane[0] = 0; p.b_start[0] = 0;   // staged row i = plane0[i]: dout row q pairs with row q
+    p.b_plane[1] = 1; p.b_start[1] = -1;  // staged row i = plane1[i - 1]: tap 0 -> row q, tap 2 -> row q + 1
     p.tap_btile[0] = 1; p.tap_shift[0] = 0;
     p.tap_btile[1] = 0; p.tap_shift[1] = 0;
     p.tap_btile[2] = 1; p.tap_shift[2] = 1;
@@ -312,6 +331,8 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   // memory address bits, so a descriptor whose start is advanced by whole 128-byte rows needs base_offset = 0;
   // base_offset = (start >> 7) & 7 gives wrong results for the shifted taps.
   p.base_offset_mode = g_dbg_base_offset_mode >= 0 ? g_dbg_base_offset_mode : 1;
+  p.fuse_taps = (ktaps == 3 && stride == 1 && c_in == 64 && g_dbg_wgrad_fuse != 0) ? 1 : 0;
+  p.tap_cols = p.fuse_taps ? 64 : 128;
   w.ok = true;
   return w;
 }

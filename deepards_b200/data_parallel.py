@@ -38,6 +38,31 @@ def shard_bounds(batch, world, rank):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def sharded_map(fn, x, group=None):
+    """Inference / GradCAM over several GPUs (replicas only, no data-path collective): this rank runs
+    `fn` on its contiguous shard of the sequences in `x` (dim 0), and the per-sequence results of all ranks are
+    gathered in order.  `fn(x_shard)` returns a tensor, or a tuple of tensors, with one leading row per sequence;
+    every rank gets the full result(s).  Shards may be ragged or empty (B < world)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return fn(x)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    b, e = shard_bounds(x.shape[0], world, rank)
+    out = fn(x[b:e])
+    single = not isinstance(out, (tuple, list))
+    outs = [out] if single else list(out)
+    sizes = [shard_bounds(x.shape[0], world, r) for r in range(world)]
+    gathered = []
+    rows = max(hi - lo for lo, hi in sizes)
+    for t in outs:
+        # ragged shards: pad to the largest shard (at most one extra row), gather equal-sized parts, trim
+        mine = torch.zeros((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        mine[:t.shape[0]].copy_(t)
+        parts = [torch.empty_like(mine) for _ in sizes]
+        dist.all_gather(parts, mine, group=group)
+        gathered.append(torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, sizes)], 0))
+    return gathered[0] if single else tuple(gathered)
+
+
 def live_ranges(layout, live_ids):
     """Merge the flat slots of the parameters in `live_ids` into maximal contiguous [begin, end) ranges."""
     ranges = []

@@ -91,6 +91,31 @@ def compute_maps(model, x, target=None, resized_len=0, want_tensors=False):
     return m
 
 
+def recording_maps(model, x, targets=None, resized_len=224, group=None):
+    """BASELINE config 5: the read maps of a whole recording, x (B, 20, 1, 224), sharded over the ranks of `group`
+    (one process per GPU, model replicated).  Sequences are independent, so every rank runs its contiguous shard through
+    one forward plan + one `dards_gradcam` launch and the uint8 maps / logits are gathered in order -- no collective on
+    the data path.  Returns (maps (B, 20, resized_len) uint8, logits (B, 2)) on every rank."""
+    from .data_parallel import shard_bounds, sharded_map
+    import torch.distributed as dist
+    tsr = None
+    if targets is not None and not isinstance(targets, (int, np.integer)):
+        tsr = torch.as_tensor(targets, dtype=torch.int32)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    lo = shard_bounds(x.shape[0], dist.get_world_size(group), dist.get_rank(group))[0] if multi else 0
+
+    def fn(shard):
+        if shard.shape[0] == 0:
+            dev = next(model.parameters()).device
+            return (torch.empty((0, x.shape[1], resized_len or 7), dtype=torch.uint8, device=dev),
+                    torch.empty((0, model.linear_final.out_features), dtype=torch.float32, device=dev))
+        t = targets if tsr is None else tsr[lo:lo + shard.shape[0]]
+        m = compute_maps(model, shard, t, resized_len=resized_len)
+        return (m.read_resized if resized_len else m.read_u8), m.logits
+
+    return sharded_map(fn, x, group)
+
+
 class GradCam(object):
     """Produces class activation maps (gradcam.py:68-107)."""
 
@@ -144,5 +169,5 @@ class FracTotalNormCam(GradCam):
         mo = compute_maps(self.model, input, (target + 1) % 2)
         t = torch.clamp_min(mt.read_raw[0], 0)
         o = torch.clamp_min(mo.read_raw[0], 0)
-        cam = (t / (o + t) * 255).to(torch.uint8)
+        cam = torch.nan_to_num(t / (o + t) * 255, nan=0.0).to(torch.uint8)
         return cam.cpu().numpy(), mt.logits[:1]

@@ -170,3 +170,39 @@ def test_bucketed_allreduce_world2_gloo():
     expect_sum = float(torch.arange(1000, dtype=torch.float32).sum()) * 3
     for rank, s, last in res:
         assert abs(s - expect_sum) < 1e-3 and last == 999 * 3
+
+
+def _gloo_map_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from deepards_b200 import data_parallel as dp
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    res = {}
+    for n in (5, 1, 4):                                  # ragged, fewer sequences than ranks, even
+        x = torch.arange(n * 3, dtype=torch.float32).view(n, 3)
+        maps, logits = dp.sharded_map(lambda s: ((s * 2).to(torch.uint8), s.sum(1, keepdim=True) + 100 * rank), x)
+        res[n] = (maps.tolist(), logits.view(-1).tolist())
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_sharded_replicas_world2_gloo():
+    """configs[3]/[4] on several GPUs = independent replicas over contiguous shards of the sequences + an ordered
+    gather of the per-sequence results; no collective on the data path."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_map_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1]                              # every rank holds the full, ordered result
+    for n in (5, 1, 4):
+        x = torch.arange(n * 3, dtype=torch.float32).view(n, 3)
+        maps, logits = res[0][n]
+        assert maps == (x * 2).to(torch.uint8).tolist()
+        owner = [0 if i < (n + 1) // 2 else 1 for i in range(n)]      # shard_bounds: remainder to the first ranks
+        assert logits == [float(x[i].sum()) + 100 * owner[i] for i in range(n)]

@@ -204,6 +204,25 @@ def test_conv_tcgen05_wgrad(case):
     assert torch.equal(got, K().conv1d_wgrad(xb, dyb, k, s, p, impl=1))  # deterministic (fixed-order split-K reduction)
 
 
+@pytest.mark.parametrize("case", [(40, 64, 64, 56, 3, 1, 1), (333, 64, 128, 28, 3, 1, 1), (2000, 64, 32, 7, 3, 1, 1)])
+def test_conv_tcgen05_wgrad_fused_taps(case):
+    """64 input channels: the three taps issued as ONE N = 192 MMA (descriptor chunk stride = one row) accumulate the
+    same products in the same order as three N = 64 MMAs -> bit-identical weight gradients."""
+    from deepards_b200 import _lib
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 9)
+    xb, dyb = cl(x.bfloat16()), cl(dy.bfloat16())
+    fused = K().conv1d_wgrad(xb, dyb, k, s, p, impl=1)
+    _lib.call("dards_tc_debug_set", 7, 0)
+    try:
+        three = K().conv1d_wgrad(xb, dyb, k, s, p, impl=1)
+    finally:
+        _lib.call("dards_tc_debug_set", 7, -1)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, three)
+    assert rel_err(fused, K().conv1d_wgrad(xb, dyb, k, s, p, impl=0)) < 2e-4
+
+
 def test_conv_tcgen05_into_channel_slice():
     case = (20, 128, 32, 14, 3, 1, 1)
     n, cin, cout, l, k, s, p = case
