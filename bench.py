@@ -127,7 +127,7 @@ def workload_config(args, cpu_sample=None):
                      "%d x %d x 1 x 224 synthetic breaths per GPU (BASELINE.json configs[1])" % (args.backbone, SEQ_PER_GPU, SUB_BATCH),
          "backbone": args.backbone, "sequences_per_gpu": SEQ_PER_GPU, "sub_batch": SUB_BATCH, "precision": "bf16 storage / "
          "tcgen05 convolutions, fp32 statistics, gradients and weights", "parallelism": "dp%d" % args.gpus,
-         "cuda_graph": (not args.no_graph) and ("whole step" if args.gpus == 1 else "per segment, NCCL between"),
+         "cuda_graph": (not args.no_graph) and ("whole step" if args.gpus == 1 else getattr(args, "dp_graph_desc", "per segment, NCCL between")),
          "l2": "working set per step (>1 GB of activations) exceeds the 126 MB L2; 4 resident input batches are rotated"}
     if cpu_sample:
         c["cpu_sample_sequences"] = cpu_sample
@@ -255,6 +255,9 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    if world > 1:
+        args.dp_graph_desc = ("whole step incl. the bucketed NCCL all-reduces (captured on the communication stream)"
+                              if trainer.dp_graph == "whole" else "per segment, NCCL between")
     seqs = SEQ_PER_GPU * world * args.steps
     value = seqs / (ms / 1e3)
     e2e_value = seqs / (ms_e2e / 1e3)

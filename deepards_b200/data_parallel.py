@@ -114,6 +114,13 @@ class DataParallelTrainer(object):
         if optimizer not in ("sgd", "adam"):
             raise ValueError("optimizer must be 'sgd' or 'adam'")
         self.use_graph = use_graph
+        # world > 1: "segments" (default) replays one graph per backward segment with the NCCL calls issued from the host
+        # in between.  "whole" (opt-in, experimental) captures the entire step INCLUDING the bucketed NCCL all-reduces
+        # (issued on the communication stream, which joins the capture through the same events that order it in eager
+        # mode) in one CUDA graph: measured no faster at 2 GPUs (164.6 k vs ~165 k seq/s) and the processes hang in
+        # destroy_process_group() at exit with torch 2.11 / NCCL 2.28, so it is not the default.
+        import os
+        self.dp_graph = os.environ.get("DEEPARDS_B200_DP_GRAPH", "segments")
         self.graph_launches = 0  # kernels launched through CUDA-graph replays (not seen by dards_launch_count)
         self.net, self.lr, self.optimizer = net, lr, optimizer
         self.momentum, self.weight_decay = momentum, weight_decay
@@ -186,6 +193,15 @@ class DataParallelTrainer(object):
         if self.use_graph and self.world == 1 and self.optimizer == "sgd":
             return self._graphed_step(plan, t_static)
         if self.use_graph and self.world > 1 and self.optimizer == "sgd":
+            if self.dp_graph == "whole":
+                try:
+                    return self._graphed_step(plan, t_static)
+                except RuntimeError as e:       # NCCL under stream capture refused: replay per segment instead
+                    import warnings
+                    warnings.warn("deepards_b200: whole-step CUDA graph with NCCL failed (%s); using per-segment graphs" % e)
+                    self.dp_graph = "segments"
+                    plan.__dict__.pop("_dp_graph", None)
+                    torch.cuda.synchronize(self.device)
             return self._segment_graphed_step(plan, t_static)
         self._step_body(plan, t_static)
         return self.loss_buf
@@ -202,9 +218,10 @@ class DataParallelTrainer(object):
         self._update(plan, st)
 
     def _graphed_step(self, plan, t_static):
-        """Single-GPU SGD step as ONE CUDA-graph launch (weight packing, forward, loss, backward, update: ~200 kernel
-        launches otherwise issued from Python).  Captured lazily on the third call for a plan, after the eager warm-up
-        steps have initialised every lazily-set function attribute and the momentum buffers."""
+        """The SGD step as ONE CUDA-graph launch (weight packing, forward, loss, backward, update: ~200 kernel
+        launches otherwise issued from Python; with more than one rank also the overlapped NCCL all-reduces, captured
+        on the communication stream).  Captured lazily on the third call for a plan, after the eager warm-up
+        steps have initialised every lazily-set function attribute, the momentum buffers and the NCCL communicator."""
         st = plan.__dict__.setdefault("_dp_graph", {"calls": 0, "graph": None, "launches": 0})
         if st["graph"] is not None:
             st["graph"].replay()
