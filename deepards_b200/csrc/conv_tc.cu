@@ -11,7 +11,10 @@
 // view (C, 2, L/2, N) and pick the parity plane (forward: of the input; dgrad: of the output), so no strided
 // gather/scatter is needed either.
 // A position tile is NB whole breaths (NB*L = 224 columns for L = 56/28/14/7), so tiles never straddle a
-// breath and there is no wasted MMA column.
+// breath and there is no wasted MMA column.  (A wave-balanced width -- 36 x 7 = 18 x 14 = 252 columns issued as
+// N = 256 MMAs, 572 tile jobs = 3.9 waves on 148 SMs instead of 640 = 4.3 -- is implemented behind debug key 8 and
+// bit-identical, but measured SLOWER: 59.8 vs 50.2 us at C=512, 35.1 vs 31.8 at C=256.  The kernel is bound by the
+// L2 -> SM operand stream, not by the per-CTA job count, and the wider tile lengthens every stage.)
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc/dealloc),
 // warps 2..9 = epilogue: TMEM -> registers -> bf16 -> shared staging tile [pos][co] -> ONE TMA store
@@ -24,7 +27,7 @@
 
 namespace dards {
 
-int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1;
+int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1, g_dbg_tile_balance = -1;
 
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
@@ -140,7 +143,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
       // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) |
+      // N = the tile's columns rounded up to 16: accumulator column j depends on B row j only, so the surplus columns
+      // (rows the TMA never wrote) cannot contaminate the real ones
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((n_tile + 15) & ~15) >> 3) << 17) |
                              ((uint32_t)(TC_BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int ew = warp - 2;
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int half = ew >> 2;      // two warps per lane quarter: each takes half of the column chunks
-    const int n_chunks = n_tile >> 4;
+    const int n_chunks = (n_tile + 15) >> 4;
     const int chunk_lo = half == 0 ? 0 : (n_chunks + 1) / 2;
     const int chunk_hi = half == 0 ? (n_chunks + 1) / 2 : n_chunks;
     const int cl = quarter * 32 + lane;  // channel within the tile
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int n = n0 + b;
-              if (n < p.n_breaths) {
+              if (n < p.n_breaths && c0 + j < n_tile) {
                 const size_t idx = ((size_t)n * p.out_l + (size_t)m * p.out_mul + p.out_off) * p.out_stride + co;
                 float val = __uint_as_float(v[j]);
                 if (p.accumulate) val += __bfloat162float(out[idx]);
@@ -532,6 +537,30 @@ static int pick_nb(int l) {
   return best;
 }
 
+// The same with the persistent schedule in mind: the kernel's makespan is (tile jobs per CTA) x (MMA columns per job).
+// Tiles of at least half the widest width are compared (narrower ones re-fetch the weights too often); `want_even`
+// keeps nb even where the long-reduction variant (4 stages, two half-tile stores) needs it.
+static int pick_nb_balanced(int l, int n_breaths, int n_co_tiles, bool want_even) {
+  const int widest = pick_nb(l);
+  if (widest <= 0 || g_dbg_tile_balance != 1) return widest;  // opt-in: measured slower (see the header comment)
+  const int sms = sm_count();
+  auto cost = [&](int nb) {
+    const long long jobs = (long long)ceil_div(n_breaths, nb) * n_co_tiles;
+    return ((jobs + sms - 1) / sms) * (long long)((nb * l + 15) & ~15);
+  };
+  int best = widest;
+  long long best_cost = cost(widest);
+  for (int nb = (widest + 1) / 2; nb * l <= TC_MAX_N; ++nb) {
+    if (want_even && (nb & 1)) continue;
+    const long long c = cost(nb);
+    if (c * 100 < best_cost * 96 || (nb > best && best != widest && c <= best_cost)) {  // >= 4 % better, or wider at par
+      best = nb;
+      best_cost = c;
+    }
+  }
+  return best;
+}
+
 struct TcProblem {
   const void* src;     // activations read by the MMA (x for fwd, dout for dgrad)
   const void* w;       // packed weights [ktaps][c_cols][c_red]
@@ -554,7 +583,7 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
   if (q.n_breaths == 0) return DARDS_OK;
   TcConvParams p = q.p;
   const int n_tile = p.nb * p.l_tile;
-  DARDS_CHECK_ARG(p.nb > 0 && n_tile % 16 == 0 && n_tile <= TC_MAX_N && n_tile >= 16,
+  DARDS_CHECK_ARG(p.nb > 0 && n_tile <= TC_MAX_N && n_tile >= 8,
                   "tcgen05 conv: unsupported position tile (%d breaths x %d)", p.nb, p.l_tile);
   DARDS_CHECK_ARG(p.n_taps > 0, "tcgen05 conv: no taps");
   // Long reductions are LOAD-LATENCY bound with 3 stages (a stage is consumed in 448 cycles, a TMA load takes ~1 us:
@@ -723,7 +752,7 @@ int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend
     p.in_start[t] = fl;
   }
   p.l_tile = l_out;
-  p.nb = pick_nb(l_out);
+  p.nb = pick_nb_balanced(l_out, n_breaths, ceil_div(c_out, TC_BLOCK_M), p.n_taps * ceil_div(c_in, TC_BLOCK_K) >= 12);
   p.out_par = 0;
   p.accumulate = addend != nullptr;
   return tc_launch(q, st);
@@ -760,7 +789,7 @@ int tc_conv_dgrad(const void* dout, const void* w_kio, void* din, const void* ad
       ++p.n_taps;
     }
     p.l_tile = l_in / stride;
-    p.nb = pick_nb(p.l_tile);
+    p.nb = pick_nb_balanced(p.l_tile, n_breaths, ceil_div(c_in, TC_BLOCK_M), p.n_taps * ceil_div(c_out, TC_BLOCK_K) >= 12);
     p.out_par = r;
     p.accumulate = addend != nullptr;
     if (p.n_taps == 0) {
@@ -783,6 +812,7 @@ int tc_debug_set(int key, int value) {
   else if (key == 5) g_dbg_conv3 = value;
   else if (key == 6) g_dbg_stages = value;
   else if (key == 7) g_dbg_wgrad_fuse = value;
+  else if (key == 8) g_dbg_tile_balance = value;
   else {
     set_error("tc_debug_set: unknown key %d", key);
     return DARDS_ERR_INVALID_ARGUMENT;

@@ -8,7 +8,7 @@
 namespace dards {
 
 // debugging overrides of descriptor fields (dards_tc_debug_set); < 0 = default
-extern int g_dbg_lbo, g_dbg_version, g_dbg_sbo, g_dbg_base_offset_mode, g_dbg_epilogue, g_dbg_conv3, g_dbg_stages, g_dbg_wgrad_fuse;
+extern int g_dbg_lbo, g_dbg_version, g_dbg_sbo, g_dbg_base_offset_mode, g_dbg_epilogue, g_dbg_conv3, g_dbg_stages, g_dbg_wgrad_fuse, g_dbg_tile_balance;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -118,16 +118,18 @@ def test_gradcam_recording_bf16_close_to_oracle():
     net = _densenet(sd, "bf16")
     x = O.synthetic_breaths(24, seed=8)
     m = G.compute_maps(net, x.cuda(), None, resized_len=224)
-    cos, agree, ref_logits = [], 0, []
+    cos, margins, ref_logits = [], [], []
     for i in range(24):
         _, raw, out = O.gradcam_read_cam(sd, x[i], int(m.target[i]))
         ref_logits.append(out[0])
         cos.append(cosine(m.read_raw[i].cpu(), raw))
-        agree += int(int(out.argmax()) == int(m.target[i]))
+        if int(out.argmax()) != int(m.target[i]):      # the predicted class may only differ at a near-tie of the logits
+            margins.append(float((out[0, 0] - out[0, 1]).abs()))
     # the bf16 tolerance of test_model_parity_gpu.py: logits within 1e-1 of the max-abs of the batch's logits
     assert rel_err(m.logits.cpu(), torch.stack(ref_logits)) <= 1e-1
     assert np.mean(cos) >= 0.98 and min(cos) >= 0.90, (np.mean(cos), min(cos))
-    assert agree >= 22
+    scale = float(torch.stack(ref_logits).abs().max())
+    assert all(mg <= 1e-1 * scale for mg in margins), (margins, scale)
     assert tuple(m.read_resized.shape) == (24, 20, 224)
 
 

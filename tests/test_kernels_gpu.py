@@ -136,6 +136,37 @@ def test_conv_tcgen05_dgrad(case, with_addend):
     assert rel_err(d_tc.float(), d_simt.float()) < (1.6e-2 if with_addend else 8e-3)
 
 
+@pytest.mark.parametrize("case", [(5120, 512, 512, 7, 3, 1, 1), (5120, 256, 256, 14, 3, 1, 1), (5120, 256, 512, 14, 3, 2, 1),
+                                  (5120, 128, 256, 28, 1, 2, 0), (1000, 256, 256, 14, 3, 1, 1), (37, 512, 512, 7, 3, 1, 1)])
+def test_conv_tcgen05_wave_balanced_tile_width(case):
+    """Opt-in tile width that follows the persistent schedule (e.g. 36 x 7 = 252 columns issued as N = 256 MMAs, 3.9
+    waves instead of 4.3; measured slower, so not the default): same per-column accumulation order, so forward, dgrad
+    and in-place dgrad are bit-identical to the widest-multiple-of-16 tiling; the direct-store epilogue agrees too."""
+    from deepards_b200 import _lib
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 3)
+    xb, dyb = cl(x.bfloat16()), cl(dy.bfloat16())
+    add = torch.randn(n, l, cin, device=DEV).bfloat16()
+    outs = {}
+    for mode in (-1, 1):  # -1: default (widest multiple of 16 columns); 1: wave-balanced
+        _lib.call("dards_tc_debug_set", 8, mode)
+        try:
+            outs[mode] = (K().conv1d_fwd(xb, w, s, p, impl=1), K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add))
+            if mode == 1 and n < 100:
+                _lib.call("dards_tc_debug_set", 4, 0)
+                outs["direct"] = K().conv1d_fwd(xb, w, s, p, impl=1)
+        finally:
+            _lib.call("dards_tc_debug_set", 8, -1)
+            _lib.call("dards_tc_debug_set", 4, -1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1][0], outs[-1][0]) and torch.equal(outs[1][1], outs[-1][1])
+    if "direct" in outs:
+        assert torch.equal(outs["direct"], outs[-1][0])
+    if n <= 1000:
+        ref = cl(F.conv1d(xb.permute(0, 2, 1).float(), w.bfloat16().float(), stride=s, padding=p))
+        assert rel_err(outs[-1][0].float(), ref) < 6e-3
+
+
 def test_conv_tcgen05_direct_store_epilogue_matches_tma_store():
     from deepards_b200 import _lib
     case = CONV_CASES[3]

@@ -173,6 +173,8 @@ if __name__ == "__main__":
         _lib.call("dards_tc_debug_set", 5, int(os.environ["KBENCH_CONV3"]))  # opt in to the single-load 3-tap kernel
     if os.environ.get("KBENCH_WGRAD_FUSE"):
         _lib.call("dards_tc_debug_set", 7, int(os.environ["KBENCH_WGRAD_FUSE"]))  # 0: three MMAs per k-step at C=64
+    if os.environ.get("KBENCH_TILE_BALANCE"):
+        _lib.call("dards_tc_debug_set", 8, int(os.environ["KBENCH_TILE_BALANCE"]))  # 1: wave-balanced tile width
     if os.environ.get("KBENCH_STAGES"):
         _lib.call("dards_tc_debug_set", 6, int(os.environ["KBENCH_STAGES"]))
     for wname in what:
