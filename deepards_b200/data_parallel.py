@@ -169,19 +169,28 @@ class DataParallelTrainer(object):
             plan._dp_buckets = make_buckets(self.total, [off for off, _ in plan.bwd_marks], self.bucket_elems)
         return plan
 
-    def train_step(self, x, target):
+    def train_step(self, x, target, global_batch=None):
         """x: this rank's (B_local, 20, 1, 224) on the device, target (B_local, 2).  Returns the device tensor
-        holding the local mean loss (no host synchronisation)."""
-        return self._train_step(x, target, None)
+        holding the local mean loss (no host synchronisation).
+        global_batch: total number of sequences over all ranks.  The reference's DataParallel computes ONE mean loss over
+        the gathered outputs (train_ards_detector.py:153-163); with equal shards that is the mean of the ranks' local means
+        (the default), with a ragged split (last batch of an epoch) pass the global size and every rank's gradient is
+        weighted by its share, B_local / global_batch."""
+        return self._train_step(x, target, None, global_batch)
 
-    def train_step_raw(self, raw, target, mu, std, padded=False):
+    def train_step_raw(self, raw, target, mu, std, padded=False, global_batch=None):
         """The same step fed with RAW float64 / float32 windows on the device: the dataset's `(data - mu) / std` +
         `.float()` (dataset.py:1375-1379) runs as the plan's input load, so the host pipeline only has to hand over
         the stored windows."""
-        return self._train_step(raw, target, (mu, std, padded))
+        return self._train_step(raw, target, (mu, std, padded), global_batch)
 
-    def _train_step(self, x, target, scaling):
+    def _train_step(self, x, target, scaling, global_batch=None):
         plan = self.plan_for(x)
+        # dlogits carries world * B_local / B_global, the update 1 / world: together the global-mean weighting
+        gs = 1.0 if global_batch is None else self.world * x.shape[0] / float(global_batch)
+        if plan.__dict__.setdefault("_dp_grad_scale", gs) != gs:
+            raise RuntimeError("deepards_b200: this plan (%d sequences per rank) was first used with a different global "
+                               "batch size; the loss scale is part of its captured CUDA graphs" % x.shape[0])
         if scaling is None:
             plan.load_input(x)
         else:
@@ -210,7 +219,7 @@ class DataParallelTrainer(object):
         st = plan._stream()
         plan.run_forward()
         _lib.call("dards_bce_with_logits", plan.logits.data_ptr(), t_static.data_ptr(), self.loss_buf.data_ptr(),
-                  plan.dlogits.data_ptr(), plan.logits.numel(), 1.0, st)
+                  plan.dlogits.data_ptr(), plan.logits.numel(), plan.__dict__.get("_dp_grad_scale", 1.0), st)
         if self.world > 1:
             self._backward_overlapped(plan)
         else:
@@ -311,7 +320,7 @@ class DataParallelTrainer(object):
                 plan.seed_dev.add_(1)
             plan.fwd.run(st)
             _lib.call("dards_bce_with_logits", plan.logits.data_ptr(), t_static.data_ptr(), self.loss_buf.data_ptr(),
-                      plan.dlogits.data_ptr(), plan.logits.numel(), 1.0, st)
+                      plan.dlogits.data_ptr(), plan.logits.numel(), plan.__dict__.get("_dp_grad_scale", 1.0), st)
 
         out["fwd"] = capture(fwd)
         # backward segments: cut after every call index that carries a mark

@@ -27,6 +27,9 @@ SEQ_LEN = 224
 
 _DTYPES = {"fp32": (torch.float32, _lib.F32), "bf16": (torch.bfloat16, _lib.BF16)}
 
+# Smallest gradient suffix (fp32 elements) worth an all-reduce bucket of its own: 4 MB, the trainer's default bucket size.
+DP_MARK_ELEMS = int(os.environ.get("DEEPARDS_B200_DP_BUCKET_ELEMS", 1 << 20))
+
 
 def _multi_rank():
     import torch.distributed as dist
@@ -153,10 +156,17 @@ class Plan(object):
         """Backward bookkeeping for the overlapped all-reduce: every gradient slot at or after `first_param`'s
         is final once the calls recorded so far have run (backward visits the layers last to first).
         With more than one rank the pending partial-sum reductions are flushed here, so that the bucket behind the mark
-        can go to the all-reduce; a single rank reduces everything in ONE launch at the end of the backward."""
+        can go to the all-reduce; a single rank reduces everything in ONE launch at the end of the backward.
+        A mark is only set once at least DP_MARK_ELEMS gradient elements have become final since the previous one:
+        every mark costs a reduction launch and a CUDA-graph boundary in the multi-GPU step, and a smaller bucket
+        would be merged by the trainer anyway (DenseNet-18's 0.86 MB of gradients are ONE bucket and ONE backward graph)."""
+        off = self.goff[id(first_param)]
+        last = self.bwd_marks[-1][0] if self.bwd_marks else self.grad_numel
+        if last - off < DP_MARK_ELEMS:
+            return
         if _multi_rank():
             self._flush_reductions()
-        self.bwd_marks.append((self.goff[id(first_param)], len(self.bwd.calls)))
+        self.bwd_marks.append((off, len(self.bwd.calls)))
 
     def grad_view(self, p):
         off = self.goff[id(p)]
