@@ -647,12 +647,7 @@ __device__ __forceinline__ float4 table_reduce64(const float* __restrict__ table
 __global__ void __launch_bounds__(256) reduce_rows_batched_kernel(const dards_reduce_desc* __restrict__ descs, int n) {
   __shared__ dards_reduce_desc d;
   __shared__ float4 scratch[256];
-  if (threadIdx.x == 0) {
-    int j = 0;
-    while (j + 1 < n && (int)blockIdx.x >= descs[j + 1].first_block) ++j;
-    d = descs[j];
-  }
-  __syncthreads();
+  find_block_desc(descs, n, &d);
   const int col0 = ((int)blockIdx.x - d.first_block) * 64;
   const float4 t = table_reduce64(d.part, d.rows, d.c, col0, [](int) { return 1.f; }, [](float v) { return v; }, scratch);
   const int ch = col0 + threadIdx.x * 4;
@@ -697,12 +692,7 @@ __global__ void __launch_bounds__(256) bn_running_update_batched_kernel(const da
                                                                         float eps) {
   __shared__ dards_running_desc d;
   __shared__ float4 scratch[256];
-  if (threadIdx.x == 0) {
-    int j = 0;
-    while (j + 1 < n && (int)blockIdx.x >= descs[j + 1].first_block) ++j;
-    d = descs[j];
-  }
-  __syncthreads();
+  find_block_desc(descs, n, &d);
   running_update_block(d, ((int)blockIdx.x - d.first_block) * 64, eps, scratch);
 }
 

@@ -66,6 +66,20 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Batched ("one launch for a whole table of tensors") kernels: block b serves the descriptor j with
+// first_block[j] <= b < first_block[j+1].  The whole CTA looks the table up in parallel -- a thread-0 linear scan is a
+// chain of up to n dependent global loads (~0.7 us each), which was most of these small kernels' run time.
+template <typename D>
+__device__ __forceinline__ void find_block_desc(const D* __restrict__ descs, int n, D* s_desc) {
+  const int b = (int)blockIdx.x;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int lo = descs[j].first_block;
+    const int hi = j + 1 < n ? descs[j + 1].first_block : 0x7fffffff;
+    if (b >= lo && b < hi) *s_desc = descs[j];  // exactly one j matches (first_block is non-decreasing)
+  }
+  __syncthreads();
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // forward / dgrad implicit GEMM of the CUDA-core path (conv_simt.cu)

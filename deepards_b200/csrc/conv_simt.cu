@@ -37,12 +37,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_conv_weights_batched_kernel(const dards_pack_desc* __restrict__ descs, int n) {
   __shared__ dards_pack_desc d;
   __shared__ float tile[PACK_TILE][PACK_TILE * PACK_MAX_TAPS + 1];
-  if (threadIdx.x == 0) {
-    int j = 0;
-    while (j + 1 < n && (int)blockIdx.x >= descs[j + 1].first_block) ++j;
-    d = descs[j];
-  }
-  __syncthreads();
+  find_block_desc(descs, n, &d);
   const int K = d.ktaps, c_in = d.c_in, c_out = d.c_out;
   const int n_co_t = (c_out + PACK_TILE - 1) / PACK_TILE;
   const int b = (int)blockIdx.x - d.first_block;

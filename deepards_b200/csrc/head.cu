@@ -71,6 +71,27 @@ __global__ void avgpool_full_bwd_kernel(const float* __restrict__ dfeat, T* __re
   }
 }
 
+// bf16, 8 channels per thread: the pooled gradient of (breath, channel vector) is read and scaled ONCE and written to
+// all l positions with 16-byte stores (the generic kernel re-reads dfeat for every position and stores 8 bytes)
+__global__ void avgpool_full_bwd_bf16x8_kernel(const float* __restrict__ dfeat, __nv_bfloat16* __restrict__ din,
+                                               long long n_breaths, int l, int c8, int din_stride) {
+  const long long total = n_breaths * c8;
+  const float inv = 1.f / (float)l;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cq = (int)(i % c8);
+    const long long n = i / c8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(dfeat + (size_t)n * c8 * 8 + cq * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(dfeat + (size_t)n * c8 * 8 + cq * 8 + 4));
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x * inv, a.y * inv), p1 = __floats2bfloat162_rn(a.z * inv, a.w * inv);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x * inv, b.y * inv), p3 = __floats2bfloat162_rn(b.z * inv, b.w * inv);
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+    v.z = *reinterpret_cast<uint32_t*>(&p2); v.w = *reinterpret_cast<uint32_t*>(&p3);
+    __nv_bfloat16* dst = din + (size_t)n * l * din_stride + cq * 8;
+    for (int q = 0; q < l; ++q) *reinterpret_cast<uint4*>(dst + (size_t)q * din_stride) = v;
+  }
+}
+
 // ---- dropout: keep-mask is a pure function of (seed, element index) ---------------------------------------
 __device__ __forceinline__ uint32_t mix32(uint64_t z) {
   // splitmix64 finaliser
@@ -123,11 +144,27 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_fwd_kernel(const float* __
 #pragma unroll
   for (int j = 0; j < LIN_MAX_OUT; ++j) acc[j] = 0.f;
   const float* f = feat + (size_t)r * k;
-  for (int i = threadIdx.x; i < k; i += LIN_THREADS) {
-    float v = f[i];
+  if ((k & 3) == 0 && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    // 16-byte loads, every load of the row independent of the others (the kernel is latency bound: one CTA per row)
+    const float4* f4 = reinterpret_cast<const float4*>(f);
+    const int k4 = k >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < k4; i += LIN_THREADS) {
+      const float4 v = __ldg(f4 + i);
 #pragma unroll
-    for (int j = 0; j < LIN_MAX_OUT; ++j)
-      if (j < n_out) acc[j] = fmaf(v, w[(size_t)j * k + i], acc[j]);
+      for (int j = 0; j < LIN_MAX_OUT; ++j)
+        if (j < n_out) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (size_t)j * k) + i);
+          acc[j] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[j]))));
+        }
+    }
+  } else {
+    for (int i = threadIdx.x; i < k; i += LIN_THREADS) {
+      float v = f[i];
+#pragma unroll
+      for (int j = 0; j < LIN_MAX_OUT; ++j)
+        if (j < n_out) acc[j] = fmaf(v, w[(size_t)j * k + i], acc[j]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < LIN_MAX_OUT; ++j) acc[j] = warp_sum(acc[j]);
@@ -157,21 +194,23 @@ __global__ void linear_bwd_data_kernel(const float* __restrict__ dlogits, const 
   }
 }
 
-// dw[j][k] (+)= sum_r dlogits[r][j] feat[r][k].  256 threads = 64 columns k x 4 row lanes; every thread reads its
+// dw[j][k] (+)= sum_r dlogits[r][j] feat[r][k].  256 threads = 32 columns k x 8 row lanes; every thread reads its
 // feat column once for all n_out outputs with 8 rows in flight; lane sums are combined in a fixed order -> deterministic.
+// The bias gradient (a sum over all rows of a few values) is reduced by the whole first CTA, not by n_out threads.
+constexpr int LBW_COLS = 32, LBW_LANES = 8;
 __global__ void __launch_bounds__(256) linear_bwd_weight_kernel(const float* __restrict__ dlogits,
                                                                 const float* __restrict__ feat, float* __restrict__ dw,
                                                                 float* __restrict__ db, int rows, int k, int n_out,
                                                                 int accumulate) {
-  __shared__ float red[4][LIN_MAX_OUT][64];
-  const int col = threadIdx.x & 63, ln = threadIdx.x >> 6;
-  const int kk = blockIdx.x * 64 + col;
+  __shared__ float red[LBW_LANES][LIN_MAX_OUT][LBW_COLS];
+  const int col = threadIdx.x & (LBW_COLS - 1), ln = threadIdx.x / LBW_COLS;
+  const int kk = blockIdx.x * LBW_COLS + col;
   float acc[LIN_MAX_OUT];
 #pragma unroll
   for (int j = 0; j < LIN_MAX_OUT; ++j) acc[j] = 0.f;
   if (kk < k) {
 #pragma unroll 8
-    for (int r = ln; r < rows; r += 4) {
+    for (int r = ln; r < rows; r += LBW_LANES) {
       const float f = feat[(size_t)r * k + kk];
 #pragma unroll
       for (int j = 0; j < LIN_MAX_OUT; ++j)
@@ -183,16 +222,29 @@ __global__ void __launch_bounds__(256) linear_bwd_weight_kernel(const float* __r
   __syncthreads();
   if (ln == 0 && kk < k) {
     for (int j = 0; j < n_out; ++j) {
-      const float s = red[0][j][col] + red[1][j][col] + red[2][j][col] + red[3][j][col];
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < LBW_LANES; ++q) s += red[q][j][col];
       float* o = dw + (size_t)j * k + kk;
       *o = accumulate ? *o + s : s;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < n_out && db) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < rows; ++r) s += dlogits[(size_t)r * n_out + threadIdx.x];
-    db[threadIdx.x] = accumulate ? db[threadIdx.x] + s : s;
+  if (blockIdx.x == 0 && db) {
+    __syncthreads();  // `red` is reused: [warp][j]
+    float* wred = &red[0][0][0];
+    for (int j = 0; j < n_out; ++j) {
+      float s = 0.f;
+      for (int r = threadIdx.x; r < rows; r += 256) s += dlogits[(size_t)r * n_out + j];
+      s = warp_sum(s);
+      if ((threadIdx.x & 31) == 0) wred[(threadIdx.x >> 5) * LIN_MAX_OUT + j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_out) {
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) s += wred[wv * LIN_MAX_OUT + threadIdx.x];
+      db[threadIdx.x] = accumulate ? db[threadIdx.x] + s : s;
+    }
   }
 }
 
@@ -268,6 +320,13 @@ int launch_avgpool_full_bwd(const float* dfeat, void* din, int n_breaths, int l,
                             cudaStream_t st) {
   DARDS_CHECK_ARG(c % 4 == 0 && din_stride % 4 == 0, "avgpool: channels/stride must be multiples of 4");
   if (n_breaths == 0) return DARDS_OK;
+  if (dtype == DARDS_BF16 && c % 8 == 0 && din_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(din) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dfeat) & 15) == 0) {
+    avgpool_full_bwd_bf16x8_kernel<<<grid_for((long long)n_breaths * (c / 8), 256), 256, 0, st>>>(
+        dfeat, static_cast<__nv_bfloat16*>(din), n_breaths, l, c / 8, din_stride);
+    DARDS_CHECK_LAUNCH("avgpool_full_bwd");
+    return DARDS_OK;
+  }
   int blocks = grid_for((long long)n_breaths * l * (c / 4), 256);
   DARDS_DISPATCH_DTYPE(dtype, {
     avgpool_full_bwd_kernel<T><<<blocks, 256, 0, st>>>(dfeat, static_cast<T*>(din), n_breaths, l, c / 4, din_stride);
@@ -311,7 +370,7 @@ int launch_linear_bwd(const float* dlogits, const float* feat, const float* w, f
     DARDS_CHECK_LAUNCH("linear_bwd_data");
   }
   if (dw) {
-    linear_bwd_weight_kernel<<<ceil_div(k, 64), 256, 0, st>>>(dlogits, feat, dw, db, rows, k, n_out, accumulate);
+    linear_bwd_weight_kernel<<<ceil_div(k, LBW_COLS), 256, 0, st>>>(dlogits, feat, dw, db, rows, k, n_out, accumulate);
     DARDS_CHECK_LAUNCH("linear_bwd_weight");
   }
   return DARDS_OK;
