@@ -26,6 +26,13 @@ constexpr int STEM_BS = STEM_L + 2 * STEM_PAD;       // 240: smem breath stride 
 constexpr int STEM_RUN = 28;                         // conv outputs per run; 4 runs per breath
 constexpr int STEM_MAX_GROUP = 236;                  // 236 * 240 * 4 B = 226 KB of dynamic smem
 
+// 16-byte asynchronous global -> shared copy (L2-only caching: the data is read once)
+__device__ __forceinline__ void stem_cp_async16(const void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void stem_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // group input -> zero-padded shared copy
 __device__ __forceinline__ void stem_load_group(const float* __restrict__ xg, float* xs, int group) {
   for (int i = threadIdx.x; i < group * STEM_BS; i += STEM_THREADS) {
@@ -161,7 +168,11 @@ __device__ __forceinline__ int stem_r_index(int a, int b) {  // a <= b
   return a * STEM_K - a * (a - 1) / 2 + (b - a);
 }
 
-template <typename T>
+// STAGE: the CTA's slice of dout (group x 56 rows x 16 channels) is brought into shared memory with cp.async while the
+// input moments are computed, and sweep B reads it from there.  With the gradient loaded from global memory inside the
+// sweep the kernel spent most of its time waiting on those loads (ncu: long-scoreboard stalls 5.9 per issue, issue
+// slots 47 % busy).  Groups too large for the extra 35 KB per 20 breaths use the direct path.
+template <typename T, bool STAGE>
 __global__ void __launch_bounds__(STEM_THREADS)
     stem_bwd_kernel(const T* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ save_mean,
@@ -174,6 +185,17 @@ __global__ void __launch_bounds__(STEM_THREADS)
   const int tid = threadIdx.x;
   const int c = tid % STEM_CS, rl = tid / STEM_CS;
   const int ch = blockIdx.y * STEM_CS + c;
+  T* ds = reinterpret_cast<T*>(xs + (size_t)group * STEM_BS);  // [group*56][16] staged dout slice (STAGE only)
+  if (STAGE) {
+    constexpr int EPC = 16 / (int)sizeof(T);           // elements per 16-byte chunk
+    constexpr int CPR = STEM_CS / EPC;                 // chunks per row: 2 (bf16) or 4 (fp32)
+    const T* src = dout + (size_t)g * group * STEM_LP * dout_stride + blockIdx.y * STEM_CS;
+    const int n_chunks = group * STEM_LP * CPR;
+    for (int q = tid; q < n_chunks; q += STEM_THREADS) {
+      const int row = q / CPR, part = q % CPR;
+      stem_cp_async16(ds + row * STEM_CS + part * EPC, src + (size_t)row * dout_stride + part * EPC);
+    }
+  }
   stem_load_group(x + (size_t)g * group * STEM_L, xs, group);
   __syncthreads();
   const int n_conv = group * STEM_LC;
@@ -229,10 +251,16 @@ __global__ void __launch_bounds__(STEM_THREADS)
 #pragma unroll
   for (int t = 0; t < STEM_K; ++t) gt[t] = 0.f;
   const int n_runs = group * (STEM_LC / STEM_RUN);
+  if (STAGE) {
+    stem_cp_async_wait_all();
+    __syncthreads();  // every thread's chunks have landed
+  }
+  const int dp_stride = STAGE ? STEM_CS : dout_stride;
   for (int run = rl; run < n_runs; run += STEM_LANES) {
     const int b = run >> 2, lp0 = (run & 3) * (STEM_RUN / 2);
     const float* xb = xs + b * STEM_BS + STEM_PAD + 4 * lp0 - 5;  // xw[i] = xb[i + 4j]
-    const T* dp_ptr = dout + ((size_t)(g * group + b) * STEM_LP + lp0) * dout_stride + ch;
+    const T* dp_ptr = STAGE ? ds + (b * STEM_LP + lp0) * STEM_CS + c
+                            : dout + ((size_t)(g * group + b) * STEM_LP + lp0) * dout_stride + ch;
     float xw[11];
 #pragma unroll
     for (int i = 0; i < 7; ++i) xw[i] = xb[i];
@@ -240,7 +268,7 @@ __global__ void __launch_bounds__(STEM_THREADS)
     bool okl = lp0 != 0;  // conv position -1 does not exist
 #pragma unroll
     for (int j = 0; j < STEM_RUN / 2; ++j) {
-      const float dp = Elem<T>::ld(dp_ptr + (size_t)j * dout_stride);
+      const float dp = Elem<T>::ld(dp_ptr + (size_t)j * dp_stride);
       const float2 n0 = *reinterpret_cast<const float2*>(xb + 7 + 4 * j);
       const float2 n1 = *reinterpret_cast<const float2*>(xb + 9 + 4 * j);
       xw[7] = n0.x; xw[8] = n0.y; xw[9] = n1.x; xw[10] = n1.y;
@@ -364,15 +392,28 @@ int launch_stem_bwd(const void* dout, const float* x, const float* w, const floa
   DARDS_CHECK_ARG(group > 0 && group <= STEM_MAX_GROUP - 10, "stem: BatchNorm group must be in [1, %d] breaths (got %d)",
                   STEM_MAX_GROUP - 10, group);
   if (n_groups == 0) return DARDS_OK;
-  const size_t smem = (size_t)group * STEM_BS * sizeof(float);
+  const size_t smem_x = (size_t)group * STEM_BS * sizeof(float);
   dim3 grid(n_groups, c0 / STEM_CS);
-  static size_t granted[2] = {36 * 1024, 36 * 1024};  // 9.4 KB of static smem on top
+  static size_t granted[4] = {36 * 1024, 36 * 1024, 36 * 1024, 36 * 1024};  // 9.4 KB of static smem on top
   DARDS_DISPATCH_DTYPE(dtype, {
-    int rc = stem_smem_optin(stem_bwd_kernel<T>, smem, &granted[dtype == DARDS_BF16 ? 1 : 0]);
-    if (rc) return rc;
-    stem_bwd_kernel<T><<<grid, STEM_THREADS, smem, st>>>(static_cast<const T*>(dout), x, w, gamma, beta, save_mean,
-                                                         save_rstd, dw_part, dgamma_part, dbeta_part, group, c0,
-                                                         dout_stride, pool);
+    // staged gradient slice: 16-byte aligned rows, and room for it next to the input (3 CTAs per SM at group 20)
+    const size_t smem_d = (size_t)group * STEM_LP * STEM_CS * sizeof(T);
+    const bool stage = (dout_stride * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
+                       smem_x + smem_d <= 200 * 1024;
+    const int slot = (dtype == DARDS_BF16 ? 1 : 0) + (stage ? 2 : 0);
+    if (stage) {
+      int rc = stem_smem_optin(stem_bwd_kernel<T, true>, smem_x + smem_d, &granted[slot]);
+      if (rc) return rc;
+      stem_bwd_kernel<T, true><<<grid, STEM_THREADS, smem_x + smem_d, st>>>(
+          static_cast<const T*>(dout), x, w, gamma, beta, save_mean, save_rstd, dw_part, dgamma_part, dbeta_part, group,
+          c0, dout_stride, pool);
+    } else {
+      int rc = stem_smem_optin(stem_bwd_kernel<T, false>, smem_x, &granted[slot]);
+      if (rc) return rc;
+      stem_bwd_kernel<T, false><<<grid, STEM_THREADS, smem_x, st>>>(
+          static_cast<const T*>(dout), x, w, gamma, beta, save_mean, save_rstd, dw_part, dgamma_part, dbeta_part, group,
+          c0, dout_stride, pool);
+    }
   })
   DARDS_CHECK_LAUNCH("stem_bwd");
   return DARDS_OK;
