@@ -206,20 +206,22 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int t = 0; t < p.n_taps; ++t) {
       float* dst = partial + (((size_t)split * p.n_taps + t) * p.c_out + co) * p.c_in + ci0;
-      for (int c0 = 0; c0 < ci_n; c0 += 16) {
-        uint32_t v[16];
+      for (int c0 = 0; c0 < ci_n; c0 += 32) {  // ci_n is 64 or 128: two 16-column TMEM loads per wait
+        uint32_t v[32];
         if (n_iters > 0) {
-          tmem_ld16(t_row + (uint32_t)(t * p.tap_cols) + (uint32_t)c0, v);
+          tmem_ld16(t_row + (uint32_t)(t * p.tap_cols) + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[16]>(v));
+          tmem_ld16(t_row + (uint32_t)(t * p.tap_cols) + (uint32_t)c0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0u;
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        if (co < p.c_out && ci0 + c0 < p.c_in) {  // c_in is a multiple of 16
+        if (co < p.c_out) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            if (ci0 + c0 + j < p.c_in)  // c_in is a multiple of 16
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
       }
     }
@@ -232,30 +234,38 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
   }
 }
 
-// dw[co][ci][t] (+)= sum_s partial[s][t][co][ci].  256 threads = 32 float4 columns x 8 split lanes; every lane sums
-// its splits in order (4 loads in flight) and the 8 lane sums are combined in a fixed order -> deterministic.
+// dw[co][ci][t] (+)= sum_s partial[s][t][co][ci].  256 threads = (256 / LANES) float4 columns x LANES split lanes; every
+// lane sums its splits in order and the lane sums are combined in a fixed order -> deterministic.  LANES follows the
+// split count so that every thread has ~8-16 independent 16-byte loads in flight: with 9 splits (C = 512) one lane per
+// column reads all of them at once, with 143 splits (C <= 128) eight lanes read 18 each.
+template <int LANES>
 __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                                               int splits, int ktaps, int c_in, int c_out, int accumulate) {
-  __shared__ float4 red[8][33];
+  constexpr int COLS = 256 / LANES;
+  __shared__ float4 red[LANES][COLS + 1];
   const int per = ktaps * c_in * c_out;  // multiple of 4 (c_in % 16 == 0)
-  const int col = threadIdx.x & 31, ln = threadIdx.x >> 5;
-  const int i = (blockIdx.x * 32 + col) * 4;  // index into [t][co][ci], ci fastest
+  const int col = threadIdx.x % COLS, ln = threadIdx.x / COLS;
+  const int i = (blockIdx.x * COLS + col) * 4;  // index into [t][co][ci], ci fastest
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < per) {
-#pragma unroll 4
-    for (int k = ln; k < splits; k += 8) {
+#pragma unroll 8
+    for (int k = ln; k < splits; k += LANES) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (size_t)k * per + i));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
   }
-  red[ln][col] = s;
-  __syncthreads();
+  if (LANES > 1) {
+    red[ln][col] = s;
+    __syncthreads();
+  }
   if (ln == 0 && i < per) {
-    float4 t = red[0][col];
+    float4 t = s;
+    if (LANES > 1) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
-      const float4 v = red[k][col];
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      for (int k = 1; k < LANES; ++k) {
+        const float4 v = red[k][col];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
     }
     const int ci = i % c_in, co = (i / c_in) % c_out, tap = i / (c_in * c_out);
     float* o = dw + ((size_t)co * c_in + ci) * ktaps + tap;
@@ -389,9 +399,13 @@ int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, v
   tc_wgrad_kernel<<<grid, WG_TC_THREADS, smem, st>>>(tm_a, tm_b, static_cast<float*>(workspace), p);
   DARDS_CHECK_LAUNCH("tc_wgrad");
   const int per = ktaps * c_in * c_out;
-  const int blocks = ceil_div(per, 128);
-  tc_wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(workspace), dw, w.splits, ktaps, c_in, c_out,
-                                                 accumulate);
+  const float* part = static_cast<const float*>(workspace);
+  if (w.splits <= 16)
+    tc_wgrad_reduce_kernel<1><<<ceil_div(per, 4 * 256), 256, 0, st>>>(part, dw, w.splits, ktaps, c_in, c_out, accumulate);
+  else if (w.splits <= 48)
+    tc_wgrad_reduce_kernel<4><<<ceil_div(per, 4 * 64), 256, 0, st>>>(part, dw, w.splits, ktaps, c_in, c_out, accumulate);
+  else
+    tc_wgrad_reduce_kernel<8><<<ceil_div(per, 4 * 32), 256, 0, st>>>(part, dw, w.splits, ktaps, c_in, c_out, accumulate);
   DARDS_CHECK_LAUNCH("tc_wgrad_reduce");
   return DARDS_OK;
 }
