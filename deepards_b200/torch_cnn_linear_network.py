@@ -135,3 +135,27 @@ class CNNRegressor(_HeadBase):
         if x.shape[-1] != 224:
             raise Exception('input breaths must have sequence length of 224')
         return self.linear_final(self.breath_block(x).squeeze())
+
+
+class CNNLSTMNetwork(_HeadBase):
+    """LSTM over the sequence's breath features, Linear(hidden, 2) on every step (torch_cnn_lstm_combo.py:6-50).
+    forward(x, metadata, hx_cx) -> (B, S, 2), (hx, cx).  Breath metadata is not supported on this backend (the reference
+    ignores it when it is NaN, which is what the cnn_lstm experiment files feed, torch_cnn_lstm_combo.py:36)."""
+
+    def __init__(self, breath_block, metadata_features, bm_to_linear, lstm_hidden_units):
+        super(CNNLSTMNetwork, self).__init__()
+        if metadata_features:
+            raise NotImplementedError("deepards_b200: metadata_features > 0 is not implemented")
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.lstm_hidden_units = lstm_hidden_units
+        self.lstm_layers = 1
+        self.bm_to_linear = bm_to_linear
+        self.lstm = nn.LSTM(breath_block.n_out_filters, self.lstm_hidden_units, num_layers=self.lstm_layers, batch_first=True)
+        self.linear_final = nn.Linear(self.lstm_hidden_units, 2)
+
+    def forward(self, x, metadata=None, hx_cx=None):
+        if metadata is not None and not torch.any(torch.isnan(metadata)):
+            raise NotImplementedError("deepards_b200: breath metadata is not implemented on this backend")
+        out, (hx, cx) = self.lstm(self._sequence_features(x), hx_cx)
+        return self.linear_final(out), (hx, cx)

@@ -307,7 +307,8 @@ def cnn_linear_forward(sd, x, per_breath: bool = False, head: Optional[str] = No
     x[i] of shape (20, C, 224) is one BatchNorm sub-batch.  Returns (B, 2), or
     (B, 20, 2) for the per-breath head (torch_cnn_linear_network.py:57-67).
     head: None / 'cnn_linear' / 'per_breath', or a sibling head on the same loop --
-    'to_mean' (:7-25), 'compr_to_rf' (:28-46), 'double_linear' (:70-89)."""
+    'to_mean' (:7-25), 'compr_to_rf' (:28-46), 'double_linear' (:70-89), 'lstm' (torch_cnn_lstm_combo.py:28-50,
+    zero initial state, NaN metadata; returns the (B, S, 2) per-step outputs)."""
     if x.shape[-1] != SEQ_LEN:
         raise Exception("input breaths must have sequence length of 224")
     head = head or ("per_breath" if per_breath else "cnn_linear")
@@ -324,7 +325,7 @@ def cnn_linear_forward(sd, x, per_breath: bool = False, head: Optional[str] = No
         elif head == "double_linear":
             mid = F.linear(feat, sd["linear_intermediate.weight"], sd["linear_intermediate.bias"])
             rows.append(F.linear(mid.reshape(-1).unsqueeze(0), w, b))
-        elif head in ("to_mean", "compr_to_rf"):
+        elif head in ("to_mean", "compr_to_rf", "lstm"):
             rows.append(feat.unsqueeze(0))
         else:
             raise ValueError(head)
@@ -333,7 +334,27 @@ def cnn_linear_forward(sd, x, per_breath: bool = False, head: Optional[str] = No
         return F.linear(torch.mean(out, dim=1), w, b)
     if head == "compr_to_rf":
         return F.linear(torch.median(out, dim=1)[0], w, b)
+    if head == "lstm":
+        return F.linear(lstm_forward(sd, out), w, b)
     return out
+
+
+def lstm_forward(sd, x, prefix: str = "lstm."):
+    """nn.LSTM(num_layers=1, batch_first=True) from a zero state (torch_cnn_lstm_combo.py:19, 46), restated from the
+    torch.nn.LSTM documentation: gates (i, f, g, o) = W_ih x_t + b_ih + W_hh h_{t-1} + b_hh."""
+    w_ih, w_hh = sd[prefix + "weight_ih_l0"], sd[prefix + "weight_hh_l0"]
+    b_ih, b_hh = sd[prefix + "bias_ih_l0"], sd[prefix + "bias_hh_l0"]
+    hid = w_hh.shape[1]
+    h = x.new_zeros(x.shape[0], hid)
+    c = x.new_zeros(x.shape[0], hid)
+    outs = []
+    for t in range(x.shape[1]):
+        gates = F.linear(x[:, t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        i, f, g, o = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h.unsqueeze(1))
+    return torch.cat(outs, 1)
 
 
 def regressor_forward(sd, x, **kw):

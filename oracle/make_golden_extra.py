@@ -149,6 +149,7 @@ def sibling_heads():
     from deepards.models.resnet import resnet18 as ref_resnet18
     from deepards.models import torch_cnn_linear_network as RN
     from deepards.models.torch_cnn_bm_regressor import CNNRegressor as RefCNNRegressor
+    from deepards.models.torch_cnn_lstm_combo import CNNLSTMNetwork as RefCNNLSTMNetwork
     rec = {}
     x = O.synthetic_breaths(2, seed=55)
     t = O.synthetic_targets(2, seed=55)
@@ -157,7 +158,8 @@ def sibling_heads():
     for kind, make in (("to_mean", lambda bb: RN.CNNLinearToMean(bb)),
                        ("compr_to_rf", lambda bb: RN.CNNLinearComprToRF(bb)),
                        ("double_linear", lambda bb: RN.CNNDoubleLinearNetwork(bb, 20, 0)),
-                       ("regressor", lambda bb: RefCNNRegressor(bb, 3))):
+                       ("regressor", lambda bb: RefCNNRegressor(bb, 3)),
+                       ("lstm", lambda bb: RefCNNLSTMNetwork(bb, 0, False, 32))):
         model = make(ref_resnet18(initial_planes=16))
         sd = dict(base)
         if kind == "double_linear":
@@ -168,10 +170,20 @@ def sibling_heads():
         if kind == "regressor":
             sd["linear_final.weight"] = torch.randn(3, 128, generator=gen) * 0.1
             sd["linear_final.bias"] = torch.randn(3, generator=gen) * 0.1
+        if kind == "lstm":
+            sd["linear_final.weight"] = torch.randn(2, 32, generator=gen) * 0.1
+            sd["linear_final.bias"] = torch.randn(2, generator=gen) * 0.1
+            for k, shape in (("lstm.weight_ih_l0", (128, 128)), ("lstm.weight_hh_l0", (128, 32)),
+                             ("lstm.bias_ih_l0", (128,)), ("lstm.bias_hh_l0", (128,))):
+                sd[k] = torch.randn(*shape, generator=gen) * 0.1
         model.load_state_dict(sd, strict=True)
         model.train()
         model.zero_grad()
-        if kind == "regressor":
+        if kind == "lstm":
+            # train_ards_detector.py feeds NaN metadata and no initial state for cnn_lstm
+            out, _ = model(x, torch.tensor(float("nan")), None)
+            loss = torch.nn.BCEWithLogitsLoss()(out, t.unsqueeze(1).repeat(1, 20, 1))
+        elif kind == "regressor":
             xin = x.reshape(40, 1, 224)
             tgt = torch.randn(40, 3, generator=gen)
             out = model(xin, None)
@@ -188,13 +200,13 @@ def sibling_heads():
             if p.grad is None:
                 continue
             g = p.grad.detach().reshape(-1).numpy()
-            if name.startswith("linear") or name in ("breath_block.conv1.weight", "breath_block.bn1.weight"):
+            if name.startswith(("linear", "lstm")) or name in ("breath_block.conv1.weight", "breath_block.bn1.weight"):
                 rec[kind + "/grad/" + name] = g.reshape(p.shape).copy()
             elif name.endswith("conv2.weight"):
                 rec[kind + "/gradsample/" + name] = g[::61].copy()
                 rec[kind + "/gradmax/" + name] = np.array(np.abs(g).max())
         for k, v in sd.items():
-            if k.startswith("linear"):
+            if k.startswith(("linear", "lstm")):
                 rec[kind + "/sd/" + k] = v.numpy()
     rec["x"] = x.numpy()
     rec["target"] = t.numpy()

@@ -178,7 +178,7 @@ def test_train_step_from_raw_windows_equals_step_on_scaled_input():
 
 
 # ---- sibling heads -------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind", ["to_mean", "compr_to_rf", "double_linear", "regressor"])
+@pytest.mark.parametrize("kind", ["to_mean", "compr_to_rf", "double_linear", "regressor", "lstm"])
 def test_sibling_heads_match_reference(kind):
     import deepards_b200 as D
     z = _z("sibling_heads")
@@ -190,7 +190,8 @@ def test_sibling_heads_match_reference(kind):
             sd[k[len(kind) + 4:]] = torch.from_numpy(z[k])
     bb = D.resnet18(initial_planes=16)
     net = {"to_mean": lambda: D.CNNLinearToMean(bb), "compr_to_rf": lambda: D.CNNLinearComprToRF(bb),
-           "double_linear": lambda: D.CNNDoubleLinearNetwork(bb, 20, 0), "regressor": lambda: D.CNNRegressor(bb, 3)}[kind]()
+           "double_linear": lambda: D.CNNDoubleLinearNetwork(bb, 20, 0), "regressor": lambda: D.CNNRegressor(bb, 3),
+           "lstm": lambda: D.CNNLSTMNetwork(bb, 0, False, 32)}[kind]()
     assert list(net.state_dict().keys()) == list(z[kind + "/keys"])      # the reference's state_dict names and order
     net.load_state_dict(sd, strict=True)
     net = net.cuda()
@@ -200,6 +201,10 @@ def test_sibling_heads_match_reference(kind):
     if kind == "regressor":
         out = net(x.reshape(40, 1, 224), None)
         loss = F.mse_loss(out, torch.from_numpy(z[kind + "/target"]).cuda())
+    elif kind == "lstm":
+        out, (hx, cx) = net(x, torch.tensor(float("nan")), None)
+        assert tuple(out.shape) == (2, 20, 2) and tuple(hx.shape) == (1, 2, 32)
+        loss = F.binary_cross_entropy_with_logits(out, torch.from_numpy(z["target"]).cuda().unsqueeze(1).repeat(1, 20, 1))
     else:
         out = net(x, None)
         loss = F.binary_cross_entropy_with_logits(out, torch.from_numpy(z["target"]).cuda())

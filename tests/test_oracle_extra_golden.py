@@ -63,7 +63,7 @@ def test_cam_resize_known_properties():
     assert abs(int(r[16 + 32 * 3]) - 120) <= 1                      # source pixel centres map to themselves
 
 
-@pytest.mark.parametrize("kind", ["to_mean", "compr_to_rf", "double_linear", "regressor"])
+@pytest.mark.parametrize("kind", ["to_mean", "compr_to_rf", "double_linear", "regressor", "lstm"])
 def test_oracle_sibling_heads_equal_reference(kind):
     z = _z("sibling_heads")
     sd = O.cnn_linear_state("resnet18", seed=8, bn_perturb=0.1, initial_planes=16, per_breath=True)
