@@ -157,5 +157,8 @@ class CNNLSTMNetwork(_HeadBase):
     def forward(self, x, metadata=None, hx_cx=None):
         if metadata is not None and not torch.any(torch.isnan(metadata)):
             raise NotImplementedError("deepards_b200: breath metadata is not implemented on this backend")
-        out, (hx, cx) = self.lstm(self._sequence_features(x), hx_cx)
+        feat = self._sequence_features(x)
+        # the fp32 path promises the reference's fp32 numbers: keep cuDNN's LSTM GEMMs out of TF32 (its default)
+        with torch.backends.cudnn.flags(allow_tf32=_ag.module_precision(self) == "bf16"):
+            out, (hx, cx) = self.lstm(feat, hx_cx)
         return self.linear_final(out), (hx, cx)
