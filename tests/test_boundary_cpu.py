@@ -206,3 +206,68 @@ def test_sharded_replicas_world2_gloo():
         assert maps == (x * 2).to(torch.uint8).tolist()
         owner = [0 if i < (n + 1) // 2 else 1 for i in range(n)]      # shard_bounds: remainder to the first ranks
         assert logits == [float(x[i].sum()) + 100 * owner[i] for i in range(n)]
+
+
+def test_sibling_heads_gradcam_and_scaler_boundary_on_cpu():
+    """The rows added after the core path keep the reference's names / state_dict keys and fail loudly off the GPU."""
+    import types
+    import numpy as np
+    import deepards_b200 as D
+    from deepards_b200 import gradcam as G
+    z = np.load(os.path.join(ROOT, "tests", "golden", "sibling_heads.npz"))
+    bb = D.resnet18(initial_planes=16)
+    heads = {"to_mean": D.CNNLinearToMean(bb), "compr_to_rf": D.CNNLinearComprToRF(bb),
+             "double_linear": D.CNNDoubleLinearNetwork(bb, 20, 0), "regressor": D.CNNRegressor(bb, 3),
+             "lstm": D.CNNLSTMNetwork(bb, 0, False, 32)}
+    for kind, net in heads.items():
+        assert list(net.state_dict().keys()) == list(z[kind + "/keys"]), kind    # recorded from the reference's modules
+        assert net.seq_size == 224 and net.breath_block is bb
+    with pytest.raises(Exception, match="sequence length of 224"):
+        heads["to_mean"](torch.zeros(2, 20, 1, 100), None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        heads["double_linear"](torch.zeros(2, 20, 1, 224), None)
+    with pytest.raises(NotImplementedError):
+        D.CNNLSTMNetwork(bb, 3, False, 32)
+    fake = types.ModuleType("train_ards_detector")
+    fake.base_networks = {}
+    D.install(fake)
+    for name in ("CNNLinearToMean", "CNNLinearComprToRF", "CNNDoubleLinearNetwork", "CNNRegressor", "CNNLSTMNetwork"):
+        assert getattr(fake, name) is getattr(D, name)
+    assert D.network_heads["cnn_lstm"] is D.CNNLSTMNetwork
+    # GradCAM: same class names and methods as deepards/gradcam.py; DenseNet only; never a CPU path
+    for cls in ("GradCam", "MaxMinNormCam", "UnNormalizedCam", "FracTotalNormCam"):
+        assert hasattr(getattr(G, cls), "generate_one_hot_grad_and_output")
+    assert hasattr(G.MaxMinNormCam, "generate_cam") and hasattr(G.MaxMinNormCam, "generate_read_cam")
+    with pytest.raises(TypeError, match="DenseNet"):
+        G.MaxMinNormCam(D.CNNLinearNetwork(bb, 20, 0)).generate_cam(torch.zeros(20, 1, 224))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.MaxMinNormCam(D.CNNLinearNetwork(D.densenet18(), 20, 0)).generate_cam(torch.zeros(20, 1, 224))
+    with pytest.raises(NotImplementedError):
+        G.FracTotalNormCam(None).generate_cam(None, 0)
+    # window scaling: the padded rule follows the dataset type string; host tensors need an explicit device
+    assert D.WindowScaler.for_dataset_type(2.0, 28.0, "padded_breath_by_breath_with_full_bm_target").padded
+    assert not D.WindowScaler.for_dataset_type(2.0, 28.0, "unpadded_centered_sequences").padded
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        D.WindowScaler(2.0, 28.0)(torch.zeros(2, 224, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        D.WindowScaler(2.0, 0.0)
+    with pytest.raises(TypeError):
+        D.WindowScaler(2.0, 28.0)(torch.zeros(2, 224, dtype=torch.int16))
+
+
+def test_data_parallel_marks_are_bucket_sized():
+    """engine.Plan.mark: a mark (= a partial-sum reduction launch + a graph boundary in the multi-GPU step) only where
+    at least one 4 MB bucket of gradients has become final; the trainer's buckets are cut at marks only."""
+    from deepards_b200 import data_parallel as dp, engine
+    assert engine.DP_MARK_ELEMS == 1 << 20
+    # ResNet-18 slot offsets of the first parameter of each block, last block first (3.89 M elements in total)
+    total = 3_893_378
+    offs = [2_318_000, 1_006_000, 612_000, 283_000, 185_000, 103_000, 78_000, 53_000]
+    marks, last = [], total
+    for off in offs:                       # the rule of Plan.mark
+        if last - off >= engine.DP_MARK_ELEMS:
+            marks.append(off)
+            last = off
+    assert marks == [2_318_000, 1_006_000]
+    assert dp.make_buckets(total, marks, 1 << 20) == [(2_318_000, total), (1_006_000, 2_318_000), (0, 1_006_000)]
+    assert dp.make_buckets(214_850, [], 1 << 20) == [(0, 214_850)]          # DenseNet-18: one bucket
