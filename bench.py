@@ -310,7 +310,7 @@ def kernel_roofline(trainer, x, t, args, steps=3):
             for name, a, e0, e1 in evs:
                 key = name
                 if name in ("dards_conv1d_fwd", "dards_conv1d_dgrad", "dards_conv1d_wgrad"):
-                    key = name + (":tcgen05" if a[-1] == 1 else ":simt")
+                    key = name + (":tcgen05" if (a[-1] & 0xff) == 1 else ":simt")
                 d = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
                 d["ms"] += e0.elapsed_time(e1)
                 d["launches"] += 1

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdeepards_b200.so")
 
 F32, BF16 = 0, 1
+HINT_LAST_USE = 0x100   # DARDS_HINT_LAST_USE: OR-ed into `impl` (conv fwd / dgrad) or `relu` (gbn_fwd)
 ABI_VERSION = 4
 
 P, I, LL, ULL, F, D = c_void_p, c_int, c_longlong, c_ulonglong, c_float, c_double
@@ -82,6 +83,10 @@ def load():
     if lib.dards_version() != ABI_VERSION:
         raise RuntimeError("deepards_b200: ABI version mismatch (library %d, binding %d)" % (lib.dards_version(), ABI_VERSION))
     _lib = lib
+    # DEEPARDS_B200_TC_DEBUG="key=value,key=value": kernel-variant switches of dards_tc_debug_set (A/B measurements)
+    for item in filter(None, os.environ.get("DEEPARDS_B200_TC_DEBUG", "").split(",")):
+        k, v = item.split("=")
+        check(lib.dards_tc_debug_set(int(k), int(v)), "dards_tc_debug_set")
     return lib
 
 

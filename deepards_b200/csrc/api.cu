@@ -28,10 +28,10 @@ long long simt_wgrad_workspace_bytes(int, int, int, int, int);
 
 int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend, int n_breaths, int l_in, int l_out,
                 int c_in, int c_out, int in_stride, int out_stride, int addend_stride, int ktaps, int stride, int pad,
-                cudaStream_t st);
+                int src_last_use, cudaStream_t st);
 int tc_conv_dgrad(const void* dout, const void* w_kio, void* din, const void* addend, int n_breaths, int l_in, int l_out,
                   int c_in, int c_out, int dout_stride, int din_stride, int addend_stride, int ktaps, int stride, int pad,
-                  cudaStream_t st);
+                  int src_last_use, cudaStream_t st);
 int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, void* workspace, long long workspace_bytes,
                   int n_breaths, int l_in, int l_out, int c_in, int c_out, int in_stride, int dout_stride, int ktaps,
                   int stride, int pad, cudaStream_t st);
@@ -107,6 +107,8 @@ int dards_pack_conv_weights_batched(const dards_pack_desc* descs_dev, int n_desc
 int dards_conv1d_fwd(const void* in, const void* w_packed, void* out, const void* addend, int n_breaths, int l_in,
                      int l_out, int c_in, int c_out, int in_stride, int out_stride, int addend_stride, int ktaps,
                      int stride, int pad, int dtype, int impl, void* stream) {
+  const int src_last_use = (impl & DARDS_HINT_LAST_USE) ? 1 : 0;
+  impl &= 0xff;
   DARDS_CHECK_ARG(in && w_packed && out, "conv1d_fwd: null pointer");
   DARDS_CHECK_ARG(n_breaths >= 0 && l_in > 0 && c_in > 0 && c_out > 0 && ktaps > 0 && stride > 0 && pad >= 0,
                   "conv1d_fwd: bad shape");
@@ -116,7 +118,7 @@ int dards_conv1d_fwd(const void* in, const void* w_packed, void* out, const void
   if (impl == 1) {
     DARDS_CHECK_ARG(dtype == DARDS_BF16, "conv1d_fwd: the tcgen05 path is bf16 only");
     return tc_conv_fwd(in, w_packed, out, addend, n_breaths, l_in, l_out, c_in, c_out, in_stride, out_stride,
-                       addend_stride, ktaps, stride, pad, S(stream));
+                       addend_stride, ktaps, stride, pad, src_last_use, S(stream));
   }
   DARDS_CHECK_ARG(impl == 0, "conv1d_fwd: unknown impl %d", impl);
   ConvGemmArgs a;
@@ -131,6 +133,8 @@ int dards_conv1d_fwd(const void* in, const void* w_packed, void* out, const void
 int dards_conv1d_dgrad(const void* dout, const void* w_packed, void* din, const void* addend, int n_breaths, int l_in,
                        int l_out, int c_in, int c_out, int dout_stride, int din_stride, int addend_stride, int ktaps,
                        int stride, int pad, int dtype, int impl, void* stream) {
+  const int src_last_use = (impl & DARDS_HINT_LAST_USE) ? 1 : 0;
+  impl &= 0xff;
   DARDS_CHECK_ARG(dout && w_packed && din, "conv1d_dgrad: null pointer");
   DARDS_CHECK_ARG(n_breaths >= 0 && l_in > 0 && c_in > 0 && c_out > 0 && ktaps > 0 && stride > 0 && pad >= 0,
                   "conv1d_dgrad: bad shape");
@@ -140,7 +144,7 @@ int dards_conv1d_dgrad(const void* dout, const void* w_packed, void* din, const 
   if (impl == 1) {
     DARDS_CHECK_ARG(dtype == DARDS_BF16, "conv1d_dgrad: the tcgen05 path is bf16 only");
     return tc_conv_dgrad(dout, w_packed, din, addend, n_breaths, l_in, l_out, c_in, c_out, dout_stride, din_stride,
-                         addend_stride, ktaps, stride, pad, S(stream));
+                         addend_stride, ktaps, stride, pad, src_last_use, S(stream));
   }
   DARDS_CHECK_ARG(impl == 0, "conv1d_dgrad: unknown impl %d", impl);
   ConvGemmArgs a;

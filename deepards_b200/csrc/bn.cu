@@ -93,6 +93,12 @@ __device__ __forceinline__ void cp_async16(const void* smem_dst, const void* gsr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
+__device__ __forceinline__ void cp_async16_pol(const void* smem_dst, const void* gsrc, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // The cached kernels are PERSISTENT: gridDim.x CTAs walk the (group, channel tile) list round-robin.  A tile is
@@ -114,8 +120,10 @@ template <typename T, int VPR, int THREADS, bool HAS_RES, bool RELU>
 __global__ void __launch_bounds__(THREADS)
     gbn_fwd_cached_kernel(const T* x, T* out, const T* res, const float* __restrict__ gamma, const float* __restrict__ beta,
                           float* __restrict__ save_mean, float* __restrict__ save_rstd, int n_groups, int rows, int c,
-                          int x_stride, int out_stride, int res_stride, float eps) {
+                          int x_stride, int out_stride, int res_stride, float eps, int x_last_use) {
   constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V;
+  // x is the convolution output saved for the backward pass: after this read it is dead until then
+  const uint64_t pol = l2_policy(x_last_use != 0);
   extern __shared__ uint4 cache[];  // [K][THREADS]
   __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
   const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(THREADS)
     const T* xp = tile_x(tile);
     if (xp) {
       uint4* slot = cache + threadIdx.x;
-      bn_for_rows(kf, tail, [&]() { cp_async16(slot, xp); slot += THREADS; xp += x_step; });
+      bn_for_rows(kf, tail, [&]() { cp_async16_pol(slot, xp, pol); slot += THREADS; xp += x_step; });
     }
   }
   for (; tile < n_tiles; tile += gridDim.x) {
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(THREADS)
       auto row = [&](const uint4& rr) {
         const uint4 raw = *slot;
         if (xn) {
-          cp_async16(slot, xn);
+          cp_async16_pol(slot, xn, pol);
           xn += x_step;
         }
         float v[V];
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(THREADS)
     } else if (xn) {
       // a thread past the last channel of THIS tile may own channels of the next one: refill only
       uint4* slot = cache + threadIdx.x;
-      bn_for_rows(kf, tail, [&]() { cp_async16(slot, xn); slot += THREADS; xn += x_step; });
+      bn_for_rows(kf, tail, [&]() { cp_async16_pol(slot, xn, pol); slot += THREADS; xn += x_step; });
     }
   }
 }
@@ -250,9 +258,11 @@ __global__ void __launch_bounds__(THREADS)
                           const float* __restrict__ beta, const float* __restrict__ save_mean,
                           const float* __restrict__ save_rstd, T* dx, int accumulate_dx, T* dres,
                           float* __restrict__ dgamma_part, float* __restrict__ dbeta_part, int n_groups, int rows, int c,
-                          int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride) {
+                          int dout_stride, int x_stride, int mask_stride, int dx_stride, int dres_stride, int l2_hint) {
   constexpr int V = Vec<T>::N, LANES = THREADS / VPR, CT = VPR * V;
   constexpr bool USE_MASK = RELU_MODE == 2;
+  // x (the saved pre-BatchNorm activation) and the ReLU mask source are read here for the last time in the step
+  const uint64_t pol = l2_policy(l2_hint != 0);
   extern __shared__ uint4 cache[];  // [NT][K][THREADS]: gradient (masked in place by sweep 1), x, [mask source]
   __shared__ float red[(THREADS / 32 + 1) * VPR * 2 * V];
   const int rl = threadIdx.x / VPR, cq = threadIdx.x % VPR;
@@ -285,8 +295,8 @@ __global__ void __launch_bounds__(THREADS)
     uint4* slot = cache + threadIdx.x;
     bn_for_rows(kf, tail, [&]() {
       cp_async16(slot, tp.g);
-      cp_async16(slot + plane, tp.x);
-      if (USE_MASK) cp_async16(slot + 2 * plane, tp.m);
+      cp_async16_pol(slot + plane, tp.x, pol);
+      if (USE_MASK) cp_async16_pol(slot + 2 * plane, tp.m, pol);
       slot += THREADS;
       tp.g += g_step;
       tp.x += x_step;
@@ -381,8 +391,8 @@ __global__ void __launch_bounds__(THREADS)
         const uint4 rg = *slot, rx = *(slot + plane);
         if (refill) {
           cp_async16(slot, tn.g);
-          cp_async16(slot + plane, tn.x);
-          if (USE_MASK) cp_async16(slot + 2 * plane, tn.m);
+          cp_async16_pol(slot + plane, tn.x, pol);
+          if (USE_MASK) cp_async16_pol(slot + 2 * plane, tn.m, pol);
           tn.g += g_step;
           tn.x += x_step;
           if (USE_MASK) tn.m += m_step;
@@ -782,7 +792,7 @@ static int bn_persistent_grid(size_t smem_dyn, size_t smem_static, int threads, 
 template <typename T, int VPR, int THREADS, bool HAS_RES, bool RELU>
 static int run_fwd_cached_v(const void* x, void* out, const void* res, const float* gamma, const float* beta,
                             float* save_mean, float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride,
-                            int res_stride, float eps, cudaStream_t st) {
+                            int res_stride, float eps, int x_last_use, cudaStream_t st) {
   static size_t granted = 32 * 1024;
   const size_t smem = (size_t)ceil_div(rows, THREADS / VPR) * THREADS * 16;
   int rc = bn_smem_optin(gbn_fwd_cached_kernel<T, VPR, THREADS, HAS_RES, RELU>, smem, &granted);
@@ -791,17 +801,17 @@ static int run_fwd_cached_v(const void* x, void* out, const void* res, const flo
   const int grid = bn_persistent_grid(smem, (THREADS / 32 + 1) * VPR * 2 * Vec<T>::N * 4, THREADS, n_tiles);
   gbn_fwd_cached_kernel<T, VPR, THREADS, HAS_RES, RELU><<<grid, THREADS, smem, st>>>(
       static_cast<const T*>(x), static_cast<T*>(out), static_cast<const T*>(res), gamma, beta, save_mean, save_rstd,
-      n_groups, rows, c, x_stride, out_stride, res_stride, eps);
+      n_groups, rows, c, x_stride, out_stride, res_stride, eps, x_last_use);
   return DARDS_OK;
 }
 
 template <typename T, int VPR, int THREADS>
 static int run_fwd_cached(const void* x, void* out, const void* res, const float* gamma, const float* beta,
                           float* save_mean, float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride,
-                          int res_stride, float eps, int relu, cudaStream_t st) {
+                          int res_stride, float eps, int relu, int x_last_use, cudaStream_t st) {
 #define BN_FWD_V(R, A)                                                                                               \
   return run_fwd_cached_v<T, VPR, THREADS, R, A>(x, out, res, gamma, beta, save_mean, save_rstd, n_groups, rows, c, \
-                                                 x_stride, out_stride, res_stride, eps, st)
+                                                 x_stride, out_stride, res_stride, eps, x_last_use, st)
   if (res) {
     if (relu) BN_FWD_V(true, true);
     BN_FWD_V(true, false);
@@ -825,7 +835,7 @@ static int run_bwd_cached_v(const void* dout, const void* x, const void* mask_sr
   gbn_bwd_cached_kernel<T, VPR, THREADS, RELU_MODE><<<grid, THREADS, smem, st>>>(
       static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(mask_src), gamma, beta, save_mean,
       save_rstd, static_cast<T*>(dx), accumulate_dx, static_cast<T*>(dres), dgamma_part, dbeta_part, n_groups, rows, c,
-      dout_stride, x_stride, mask_stride, dx_stride, dres_stride);
+      dout_stride, x_stride, mask_stride, dx_stride, dres_stride, g_dbg_l2_hint != 0 ? 1 : 0);
   return DARDS_OK;
 }
 
@@ -855,6 +865,8 @@ static int run_bwd_cached(const void* dout, const void* x, const void* mask_src,
 int launch_gbn_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta, float* save_mean,
                    float* save_rstd, int n_groups, int rows, int c, int x_stride, int out_stride, int res_stride,
                    float eps, int relu, int dtype, cudaStream_t st) {
+  const int x_last_use = ((relu & DARDS_HINT_LAST_USE) && g_dbg_l2_hint != 0) ? 1 : 0;
+  relu &= 0xff;
   const int v = vec_of(dtype);
   DARDS_CHECK_ARG(c % v == 0 && x_stride % v == 0 && out_stride % v == 0 && (!res || res_stride % v == 0),
                   "gbn_fwd: channels and strides must be multiples of %d", v);
@@ -866,7 +878,7 @@ int launch_gbn_fwd(const void* x, void* out, const void* res, const float* gamma
     int rc = DARDS_OK;
     DARDS_DISPATCH_DTYPE(dtype, {
       BN_DISPATCH_CFG(cfg, (rc = run_fwd_cached<T, VPR, THREADS>(x, out, res, gamma, beta, save_mean, save_rstd, n_groups, rows,
-                                                                 c, x_stride, out_stride, res_stride, eps, relu, st)));
+                                                                 c, x_stride, out_stride, res_stride, eps, relu, x_last_use, st)));
     })
     if (rc) return rc;
   } else {

@@ -66,6 +66,17 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// L2 eviction-priority hints for operands that are read for the LAST time (saved forward activations in the backward
+// pass): evict_first keeps them from displacing the gradients that the next kernel re-reads.  g_dbg_l2_hint: debug key 9
+// (0 = plain loads).
+extern int g_dbg_l2_hint;
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
+  uint64_t p;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 // Batched ("one launch for a whole table of tensors") kernels: block b serves the descriptor j with
 // first_block[j] <= b < first_block[j+1].  The whole CTA looks the table up in parallel -- a thread-0 linear scan is a
 // chain of up to n dependent global loads (~0.7 us each), which was most of these small kernels' run time.

@@ -28,6 +28,7 @@
 namespace dards {
 
 int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1, g_dbg_tile_balance = -1;
+int g_dbg_l2_hint = -1;
 
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
@@ -305,6 +306,7 @@ struct TcConv3Params {
   int n_cols;     // MMA N: nb*(l+2) - 2 rounded up to 16
   int n_pos_tiles, n_co_tiles;
   int accumulate;
+  int src_evict_first;  // the activation tensor is read once by this launch and not again soon: L2 evict_first loads
 };
 
 __global__ void __launch_bounds__(C3_THREADS, 1)
@@ -363,12 +365,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       const uint32_t b_tx = (uint32_t)(p.nb * lp) * 128u;
+      const uint64_t pol_x = l2_policy(p.src_evict_first != 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int co0 = (tile % p.n_co_tiles) * TC_BLOCK_M, n0 = (tile / p.n_co_tiles) * p.nb;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(emptyb(sb), phb ^ 1u);
           mbar_arrive_expect_tx(fullb(sb), b_tx);
-          tma_load_4d(b_base + sb * C3_B_BYTES, &tm_x, fullb(sb), kc * TC_BLOCK_K, 0, -1, n0);
+          tma_load_4d_pol(b_base + sb * C3_B_BYTES, &tm_x, fullb(sb), kc * TC_BLOCK_K, 0, -1, n0, pol_x);
           if (++sb == C3_B_STAGES) {
             sb = 0;
             phb ^= 1u;
@@ -669,7 +672,8 @@ static bool tc3_applicable(int l, int c_red, int ktaps, int stride, int pad) {
 }
 
 static int tc3_launch(const void* src, const void* w, void* dst, int n_breaths, int l, int c_red, int c_cols,
-                      int src_stride, int dst_stride, bool reverse_taps, bool accumulate, cudaStream_t st) {
+                      int src_stride, int dst_stride, bool reverse_taps, bool accumulate, int src_last_use,
+                      cudaStream_t st) {
   DARDS_CHECK_ARG(c_red % 8 == 0 && src_stride % 8 == 0 && dst_stride % 8 == 0,
                   "tcgen05 conv: channels/strides must be multiples of 8");
   DARDS_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
@@ -686,6 +690,8 @@ static int tc3_launch(const void* src, const void* w, void* dst, int n_breaths, 
   p.n_pos_tiles = ceil_div(n_breaths, nb);
   p.n_co_tiles = ceil_div(c_cols, TC_BLOCK_M);
   p.accumulate = accumulate ? 1 : 0;
+  // every activation byte is fetched once only when there is a single output-channel tile
+  p.src_evict_first = (src_last_use && p.n_co_tiles == 1 && g_dbg_l2_hint != 0) ? 1 : 0;
   for (int t = 0; t < 3; ++t) p.w_tap[t] = reverse_taps ? 2 - t : t;
   CUtensorMap tm_w, tm_x, tm_o;
   {
@@ -727,7 +733,7 @@ static int tc3_launch(const void* src, const void* w, void* dst, int n_breaths, 
 
 int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend, int n_breaths, int l_in, int l_out,
                 int c_in, int c_out, int in_stride, int out_stride, int addend_stride, int ktaps, int stride, int pad,
-                cudaStream_t st) {
+                int src_last_use, cudaStream_t st) {
   DARDS_CHECK_ARG(stride == 1 || stride == 2, "tcgen05 conv: stride must be 1 or 2");
   DARDS_CHECK_ARG(ktaps <= TC_MAX_TAPS, "tcgen05 conv: at most %d taps", TC_MAX_TAPS);
   if (addend != nullptr && (addend != out || addend_stride != out_stride)) {
@@ -735,7 +741,8 @@ int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend
     return DARDS_ERR_UNSUPPORTED;
   }
   if (tc3_applicable(l_in, c_in, ktaps, stride, pad) && l_in == l_out)
-    return tc3_launch(in, w_koi, out, n_breaths, l_in, c_in, c_out, in_stride, out_stride, false, addend != nullptr, st);
+    return tc3_launch(in, w_koi, out, n_breaths, l_in, c_in, c_out, in_stride, out_stride, false, addend != nullptr,
+                      src_last_use, st);
   TcProblem q{};
   q.src = in; q.w = w_koi; q.dst = out;
   q.n_breaths = n_breaths; q.l_src = l_in; q.src_planes = stride; q.l_dst = l_out; q.dst_planes = 1;
@@ -760,7 +767,7 @@ int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend
 
 int tc_conv_dgrad(const void* dout, const void* w_kio, void* din, const void* addend, int n_breaths, int l_in, int l_out,
                   int c_in, int c_out, int dout_stride, int din_stride, int addend_stride, int ktaps, int stride, int pad,
-                  cudaStream_t st) {
+                  int src_last_use, cudaStream_t st) {
   DARDS_CHECK_ARG(stride == 1 || stride == 2, "tcgen05 conv: stride must be 1 or 2");
   DARDS_CHECK_ARG(ktaps <= TC_MAX_TAPS, "tcgen05 conv: at most %d taps", TC_MAX_TAPS);
   DARDS_CHECK_ARG(l_in % stride == 0 && l_in / stride == l_out, "tcgen05 dgrad: needs l_in == stride * l_out");
@@ -769,7 +776,8 @@ int tc_conv_dgrad(const void* dout, const void* w_kio, void* din, const void* ad
     return DARDS_ERR_UNSUPPORTED;
   }
   if (tc3_applicable(l_in, c_out, ktaps, stride, pad))
-    return tc3_launch(dout, w_kio, din, n_breaths, l_in, c_out, c_in, dout_stride, din_stride, true, addend != nullptr, st);
+    return tc3_launch(dout, w_kio, din, n_breaths, l_in, c_out, c_in, dout_stride, din_stride, true, addend != nullptr,
+                      src_last_use, st);
   // din[p = stride*m + r] = sum over taps t with (r + pad - t) % stride == 0 of dout[m + (r+pad-t)/stride] * W_t:
   // one launch per output parity plane r; reduction over c_out.
   for (int r = 0; r < stride; ++r) {
@@ -813,6 +821,7 @@ int tc_debug_set(int key, int value) {
   else if (key == 6) g_dbg_stages = value;
   else if (key == 7) g_dbg_wgrad_fuse = value;
   else if (key == 8) g_dbg_tile_balance = value;
+  else if (key == 9) g_dbg_l2_hint = value;
   else {
     set_error("tc_debug_set: unknown key %d", key);
     return DARDS_ERR_INVALID_ARGUMENT;

@@ -55,6 +55,7 @@ struct WgTcParams {
   int base_offset_mode;        // 1 (default): base_offset 0;  0: (start >> 7) & 7 -- kept for the probe only
   int fuse_taps;               // 1: the 3 taps are the 3 column chunks of one N = 192 MMA (c_in == 64, stride 1)
   int tap_cols;                // TMEM column distance between the taps' accumulators (128, or 64 when fused)
+  int l2_hint;                 // 1: the saved input activations (their last use) are loaded with L2 evict_first priority
 };
 
 __global__ void __launch_bounds__(WG_TC_THREADS, 1)
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)rows * 128u * (uint32_t)(co_chunks + p.n_btiles * ci_chunks);
+      const uint64_t pol_b = l2_policy(p.l2_hint != 0);
       for (int it = 0; it < n_iters; ++it) {
         const int n0 = (u_begin + it) * p.nb;
         mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
         for (int b = 0; b < p.n_btiles; ++b) {
           const uint32_t sb = sa + p.a_bytes + b * p.b_bytes;
           for (int c = 0; c < ci_chunks; ++c)
-            tma_load_4d(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0);
+            tma_load_4d_pol(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0, pol_b);
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -343,6 +345,7 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   p.base_offset_mode = g_dbg_base_offset_mode >= 0 ? g_dbg_base_offset_mode : 1;
   p.fuse_taps = (ktaps == 3 && stride == 1 && c_in == 64 && g_dbg_wgrad_fuse != 0) ? 1 : 0;
   p.tap_cols = p.fuse_taps ? 64 : 128;
+  p.l2_hint = g_dbg_l2_hint != 0 ? 1 : 0;
   w.ok = true;
   return w;
 }

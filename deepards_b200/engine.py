@@ -193,20 +193,25 @@ class Plan(object):
             return ((c.k == 3 and c.pad == 1) or (c.k == 1 and c.pad == 0)) and c.cin % 16 == 0 and c.cout % 8 == 0
         return c.cin % 8 == 0 and c.cout % 8 == 0
 
-    def conv_fwd(self, c, src, src_stride, dst, dst_stride, l_in, dst_ptr_off=0):
+    def conv_fwd(self, c, src, src_stride, dst, dst_stride, l_in, dst_ptr_off=0, src_last_use=False):
+        """src_last_use: no later kernel of the forward pass reads `src` (L2 eviction hint, DARDS_HINT_LAST_USE)."""
         l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
         tc = self._tc_ok(c, "fwd")
         w = c.koi if tc else c.kio
         self.fwd.add("dards_conv1d_fwd", src, w.data_ptr(), dst + dst_ptr_off, None, self.N, l_in, l_out, c.cin, c.cout,
-                     src_stride, dst_stride, 0, c.k, c.stride, c.pad, self.dt, 1 if tc else 0)
+                     src_stride, dst_stride, 0, c.k, c.stride, c.pad, self.dt,
+                     (1 if tc else 0) | (_lib.HINT_LAST_USE if src_last_use else 0))
         return l_out
 
-    def conv_dgrad(self, c, dout, dout_stride, din, din_stride, l_in, addend=None, addend_stride=0):
+    def conv_dgrad(self, c, dout, dout_stride, din, din_stride, l_in, addend=None, addend_stride=0, src_last_use=True):
+        """src_last_use: the weight gradient of the same layer has already consumed `dout` (every plan records wgrad
+        before dgrad), so this is its last reader."""
         l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
         tc = self._tc_ok(c, "dgrad")
         w = c.kio if tc else c.koi
         self.bwd.add("dards_conv1d_dgrad", dout, w.data_ptr(), din, addend, self.N, l_in, l_out, c.cin, c.cout,
-                     dout_stride, din_stride, addend_stride, c.k, c.stride, c.pad, self.dt, 1 if tc else 0)
+                     dout_stride, din_stride, addend_stride, c.k, c.stride, c.pad, self.dt,
+                     (1 if tc else 0) | (_lib.HINT_LAST_USE if src_last_use else 0))
 
     def conv_wgrad(self, c, src, src_stride, dout, dout_stride, l_in):
         l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
@@ -228,11 +233,13 @@ class Plan(object):
     def stats(self, c):
         return self.new((self.G, c), torch.float32), self.new((self.G, c), torch.float32)
 
-    def gbn_fwd(self, bn, x, x_stride, out, out_stride, rows, c, relu, res=None, res_stride=0):
+    def gbn_fwd(self, bn, x, x_stride, out, out_stride, rows, c, relu, res=None, res_stride=0, x_last_use=True):
+        """x_last_use: x is a convolution output that nothing else reads before the backward pass (False for DenseNet's
+        concatenation buffer, which the following layers read again)."""
         mean, rstd = self.stats(c)
         self.fwd.add("dards_gbn_fwd", x, out, res, bn.weight.data_ptr(), bn.bias.data_ptr(), mean.data_ptr(),
-                     rstd.data_ptr(), self.G, rows, c, x_stride, out_stride, res_stride, BN_EPS, 1 if relu else 0,
-                     self.dt)
+                     rstd.data_ptr(), self.G, rows, c, x_stride, out_stride, res_stride, BN_EPS,
+                     (1 if relu else 0) | (_lib.HINT_LAST_USE if x_last_use else 0), self.dt)
         self._note_running(bn, mean, rstd, rows, c)
         return mean, rstd
 
@@ -375,7 +382,7 @@ class Plan(object):
                 a1 = self.new((N, lo, cout))
                 st1 = self.gbn_fwd(blk.bn1, y1.data_ptr(), cout, a1.data_ptr(), cout, self.group * lo, cout, True)
                 y2 = self.new((N, lo, cout))
-                self.conv_fwd(c2, a1.data_ptr(), cout, y2.data_ptr(), cout, lo)
+                self.conv_fwd(c2, a1.data_ptr(), cout, y2.data_ptr(), cout, lo, src_last_use=True)
                 out = self.new((N, lo, cout))
                 if blk.downsample is not None:
                     cd = self.conv(blk.downsample[0])
@@ -469,12 +476,12 @@ class Plan(object):
                 mid, g = c1.cout, c2.cout
                 rows = self.group * L
                 a = self.new((N, L, cin))
-                st1 = self.gbn_fwd(layer.norm1, cat.data_ptr(), ctot, a.data_ptr(), cin, rows, cin, True)
+                st1 = self.gbn_fwd(layer.norm1, cat.data_ptr(), ctot, a.data_ptr(), cin, rows, cin, True, x_last_use=False)
                 y1 = self.new((N, L, mid))
-                self.conv_fwd(c1, a.data_ptr(), cin, y1.data_ptr(), mid, L)
+                self.conv_fwd(c1, a.data_ptr(), cin, y1.data_ptr(), mid, L, src_last_use=True)
                 b = self.new((N, L, mid))
                 st2 = self.gbn_fwd(layer.norm2, y1.data_ptr(), mid, b.data_ptr(), mid, rows, mid, True)
-                self.conv_fwd(c2, b.data_ptr(), mid, cat.data_ptr(), ctot, L, dst_ptr_off=cin * esz)
+                self.conv_fwd(c2, b.data_ptr(), mid, cat.data_ptr(), ctot, L, dst_ptr_off=cin * esz, src_last_use=True)
                 seed = None
                 drop_p = float(getattr(layer, "drop_rate", 0.0)) if self.dropout else 0.0
                 if drop_p > 0.0:
@@ -496,9 +503,9 @@ class Plan(object):
                 ct = self.conv(t.conv)
                 rows = self.group * L
                 a = self.new((N, L, ctot))
-                stt = self.gbn_fwd(t.norm, cat.data_ptr(), ctot, a.data_ptr(), ctot, rows, ctot, True)
+                stt = self.gbn_fwd(t.norm, cat.data_ptr(), ctot, a.data_ptr(), ctot, rows, ctot, True, x_last_use=False)
                 y = self.new((N, L, ct.cout))
-                self.conv_fwd(ct, a.data_ptr(), ctot, y.data_ptr(), ct.cout, L)
+                self.conv_fwd(ct, a.data_ptr(), ctot, y.data_ptr(), ct.cout, L, src_last_use=True)
                 nxt_layers = list(blocks[bi + 1][1].children())
                 ntot = ct.cout + nxt_layers[0].conv2.out_channels * len(nxt_layers)
                 ncat = self.new((N, L // 2, ntot), zero=True)
@@ -516,13 +523,14 @@ class Plan(object):
         rows = self.group * L
         if self.mode == "features":
             self.feat_map = self.new((N, L, f))
-            st5 = self.gbn_fwd(feats.norm5, cat.data_ptr(), ctot, self.feat_map.data_ptr(), f, rows, f, False)
+            st5 = self.gbn_fwd(feats.norm5, cat.data_ptr(), ctot, self.feat_map.data_ptr(), f, rows, f, False,
+                               x_last_use=False)
             self.dfeat_map = self.new((N, L, f))
             d_act, relu5 = self.dfeat_map, 0
             self.out_features = f
         else:
             act = self.new((N, L, f))
-            st5 = self.gbn_fwd(feats.norm5, cat.data_ptr(), ctot, act.data_ptr(), f, rows, f, True)
+            st5 = self.gbn_fwd(feats.norm5, cat.data_ptr(), ctot, act.data_ptr(), f, rows, f, True, x_last_use=False)
             self._head_fwd(act.data_ptr(), f, L, f)
             self.sites["relu5"] = act
             d_act, relu5 = self.scratch("d_act", (N, L, f)), 1

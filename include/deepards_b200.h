@@ -43,6 +43,12 @@ typedef enum dards_status {
 
 typedef enum dards_dtype { DARDS_F32 = 0, DARDS_BF16 = 1 } dards_dtype;
 
+/* Optional flag, OR-ed into the `impl` argument of dards_conv1d_fwd / dards_conv1d_dgrad and into the `relu` argument of
+ * dards_gbn_fwd: the source activation tensor of this call is not read again before it would leave the L2 anyway (its
+ * last use in the forward or in the backward pass).  Kernels that read every source byte once load it with L2
+ * evict_first priority, so that it does not displace tensors the following kernels re-read.  Purely a performance hint. */
+#define DARDS_HINT_LAST_USE 0x100
+
 /* ---- library ---------------------------------------------------------------------- */
 int dards_version(void);                 /* ABI version, bumped on any signature change */
 const char* dards_last_error(void);      /* thread-local, never NULL */
@@ -249,7 +255,7 @@ int dards_gradcam(const dards_gradcam_desc* desc /* HOST struct, read during the
 /* ---- debugging ----------------------------------------------------------------------- */
 /* Overrides one field of the tcgen05 shared-memory / instruction descriptors (key: 0 = LBO field,
  * 1 = version field, 2 = SBO field for K-major tiles; 4 = epilogue (0 direct stores, 1 TMA store); 5 = 0 | 1 forces
- * the single-load 3-tap kernel off | on for every k3/s1 layer (default: reductions over <= 128 channels), 6 = 3 pins the operand ring to 3 stages, 7 = 0 issues the 3 wgrad taps of 64-channel layers as 3 MMAs instead of one N = 192 MMA, 8 = 1 opts in to the wave-balanced position-tile width of the wide convolution kernel (measured slower); value < 0 restores the default).  Only the unit tests and probes use it. */
+ * the single-load 3-tap kernel off | on for every k3/s1 layer (default: reductions over <= 128 channels), 6 = 3 pins the operand ring to 3 stages, 7 = 0 issues the 3 wgrad taps of 64-channel layers as 3 MMAs instead of one N = 192 MMA, 8 = 1 opts in to the wave-balanced position-tile width of the wide convolution kernel (measured slower), 9 = 0 loads last-use operands of the backward pass without the L2 evict_first hint; value < 0 restores the default).  Only the unit tests and probes use it. */
 int dards_tc_debug_set(int key, int value);
 
 #ifdef __cplusplus
