@@ -44,35 +44,66 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  One long-running
+    `nvidia-smi -lms 25` process streams a line every 25 ms (starting a new process per sample takes ~100 ms, about as
+    long as a short timed region); one process per sample runs next to it in case the stream is block-buffered.
+    `mark()` brackets the timed regions: the summary uses the samples taken inside them (all samples if none fell inside)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.proc, self.windows = index, [], False, None, []
+
+    def _parse(self, line):
+        parts = [s.strip() for s in line.strip().split(",")]
+        if len(parts) >= 7:
+            self.rows.append((time.perf_counter(), parts))
+
+    def _stream(self, cmd):
+        try:
+            self.proc = subprocess.Popen(cmd + ["-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                         bufsize=1)
+            for line in self.proc.stdout:
+                self._parse(line)
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
 
     def run(self):
-        while not self.stop_flag:
+        cmd = ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"]
+        threading.Thread(target=self._stream, args=(cmd,), daemon=True).start()   # dense samples, if its output is unbuffered
+        while not self.stop_flag:      # and one process per sample (~100 ms each), which always works
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                self._parse(subprocess.run(cmd, capture_output=True, text=True, timeout=5).stdout)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        self.stop_flag = True
+        try:
+            if self.proc is not None:
+                self.proc.terminate()
+        except Exception:
+            pass
+        self.join(timeout=3)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if any(a <= t <= b for a, b in self.windows)]
+        rows = inside or [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(r[col].lower().startswith("active") for r in self.rows):
+            if any(r[col].lower().startswith("active") for r in rows):
                 reasons.append(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows), "samples_in_timed_region": len(inside)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -179,6 +210,8 @@ def run_b200(args):
     xs = [x.to(dev) for x in xs_host]
     ts = [t.to(dev) for t in ts_host]
 
+    sampler_ref = [None]
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -186,12 +219,15 @@ def run_b200(args):
 
     def timed(fn, steps):
         barrier()
+        t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
         barrier()
+        if sampler_ref[0] is not None:
+            sampler_ref[0].mark(t0, time.perf_counter())
         ms = e0.elapsed_time(e1)
         if world > 1:
             tms = torch.tensor([ms], device=dev)
@@ -226,11 +262,12 @@ def run_b200(args):
         prefetch(i + 1)          # overlaps this step's kernels; buffer (i+1)%2 was consumed by step i-1, which is complete
         cur.synchronize()        # the trainer reads the loss every step
 
-    for i in range(max(args.warmup, 3)):
-        resident_step(i)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.start()            # started before the warm-up so that it is streaming by the time the clock starts
+        sampler_ref[0] = sampler
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
     l0, g0 = lib.dards_launch_count(), trainer.graph_launches
     ms = timed(resident_step, args.steps)
     launches = (lib.dards_launch_count() - l0) + (trainer.graph_launches - g0)
@@ -244,8 +281,7 @@ def run_b200(args):
 
     ms_e2e = timed(e2e_timed_step, args.steps)
     if sampler:
-        sampler.stop_flag = True
-        sampler.join(timeout=3)
+        sampler.stop()
     final_loss = float(trainer.loss_buf)
 
     # ---- per-kernel timing for the roofline (extra, untimed-for-throughput steps) ---------------------------
