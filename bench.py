@@ -359,6 +359,15 @@ def kernel_roofline(trainer, x, t, args, steps=3):
                     n, l_in, l_out, cin, cout, k = a[6], a[7], a[8], a[9], a[10], a[13]
                     d["flops"] += 2.0 * n * l_out * cin * cout * k
                     d["bytes"] += esz * n * (l_in * cin + l_out * cout)
+                elif name == "dards_conv1d_bn_fwd":
+                    # convolution + BatchNorm in one kernel: reads the input, writes y (kept for the backward) and, when the
+                    # whole normalisation runs in the epilogue, the activation (+ reads the residual)
+                    n, l_in, l_out, cin, cout, k = a[10], a[12], a[13], a[14], a[15], a[20]
+                    d["flops"] += 2.0 * n * l_out * cin * cout * k
+                    d["bytes"] += esz * n * (l_in * cin + l_out * cout * (1 + (1 if a[3] else 0) + (1 if a[4] else 0)))
+                elif name == "dards_gbn_apply_fwd":
+                    g, rows, c = a[16], a[17], a[18]
+                    d["bytes"] += esz * g * rows * c * (2 + (1 if a[2] else 0) + (1 if a[9] else 0))
                 elif name == "dards_gbn_fwd":
                     # algorithmic traffic: x read once, out written once (+ the residual read)
                     g, rows, c = a[7], a[8], a[9]

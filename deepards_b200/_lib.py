@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdeepards_b200.so")
 
 F32, BF16 = 0, 1
 HINT_LAST_USE = 0x100   # DARDS_HINT_LAST_USE: OR-ed into `impl` (conv fwd / dgrad) or `relu` (gbn_fwd)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 P, I, LL, ULL, F, D = c_void_p, c_int, c_longlong, c_ulonglong, c_float, c_double
 
@@ -37,6 +37,10 @@ _SIGNATURES = {
     "dards_conv1d_dgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "dards_conv1d_wgrad": [P, P, P, I, P, LL, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "dards_conv1d_wgrad_workspace_bytes": [I, I, I, I, I, I],
+    "dards_conv1d_bn_mode": [I, I, I, I, I, I, I, I, I, I],
+    "dards_conv1d_bn_part_entries": [I, I, I, I, I, I, I, I, I],
+    "dards_conv1d_bn_fwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, F, I, I, P],
+    "dards_gbn_apply_fwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, I, P, P, I, I, I, I, I, I, I, F, I, I, P],
     "dards_gbn_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, P],
     "dards_gbn_bwd": [P, P, P, P, P, P, P, P, I, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "dards_reduce_rows": [P, P, I, I, I, P],

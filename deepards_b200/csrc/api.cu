@@ -37,6 +37,18 @@ int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, v
                   int stride, int pad, cudaStream_t st);
 long long tc_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps);
 int tc_debug_set(int key, int value);
+int tc_conv_bn_mode(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride, int pad);
+int tc_conv_bn_part_entries(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride,
+                            int pad);
+int tc_conv_bn_fwd(const void* in, const void* w_koi, void* y, void* out, const void* res, const float* gamma,
+                   const float* beta, float* save_mean, float* save_rstd, float* part, int n_breaths, int group, int l_in,
+                   int l_out, int c_in, int c_out, int in_stride, int y_stride, int out_stride, int res_stride, int ktaps,
+                   int stride, int pad, float eps, int relu, int src_last_use, cudaStream_t st);
+int launch_gbn_apply_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta, const float* part,
+                         int entries, float* save_mean, float* save_rstd, const void* x2, const float* gamma2,
+                         const float* beta2, const float* part2, int entries2, float* save_mean2, float* save_rstd2,
+                         int n_groups, int rows, int c, int x_stride, int out_stride, int res_stride, int x2_stride, float eps,
+                         int relu, cudaStream_t st);
 
 int launch_gbn_fwd(const void*, void*, const void*, const float*, const float*, float*, float*, int, int, int, int, int,
                    int, float, int, int, cudaStream_t);
@@ -76,7 +88,7 @@ using namespace dards;
 
 extern "C" {
 
-int dards_version(void) { return 4; }
+int dards_version(void) { return 5; }
 
 const char* dards_last_error(void) { return g_err; }
 
@@ -179,6 +191,48 @@ int dards_conv1d_wgrad(const void* in, const void* dout, float* dw, int accumula
 long long dards_conv1d_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps, int impl) {
   if (impl == 1) return tc_wgrad_workspace_bytes(n_breaths, l_out, c_in, c_out, ktaps);
   return simt_wgrad_workspace_bytes(n_breaths, l_out, c_in, c_out, ktaps);
+}
+
+int dards_conv1d_bn_mode(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride,
+                         int pad, int dtype) {
+  if (dtype != DARDS_BF16) return 0;
+  return tc_conv_bn_mode(n_breaths, group, l_in, l_out, c_in, c_out, ktaps, stride, pad);
+}
+
+int dards_conv1d_bn_part_entries(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps,
+                                 int stride, int pad) {
+  return tc_conv_bn_part_entries(n_breaths, group, l_in, l_out, c_in, c_out, ktaps, stride, pad);
+}
+
+int dards_conv1d_bn_fwd(const void* in, const void* w_koi, void* y, void* out, const void* res, const float* gamma,
+                        const float* beta, float* save_mean, float* save_rstd, float* part, int n_breaths, int group,
+                        int l_in, int l_out, int c_in, int c_out, int in_stride, int y_stride, int out_stride,
+                        int res_stride, int ktaps, int stride, int pad, float eps, int relu, int dtype, void* stream) {
+  const int src_last_use = (relu & DARDS_HINT_LAST_USE) ? 1 : 0;
+  relu &= 0xff;
+  DARDS_CHECK_ARG(in && w_koi && y, "conv1d_bn_fwd: null pointer");
+  DARDS_CHECK_ARG(dtype == DARDS_BF16, "conv1d_bn_fwd: the fused tcgen05 path is bf16 only");
+  DARDS_CHECK_ARG(n_breaths > 0 && group > 0 && l_in > 0 && c_in > 0 && c_out > 0 && ktaps > 0 && stride > 0 && pad >= 0,
+                  "conv1d_bn_fwd: bad shape");
+  DARDS_CHECK_ARG(l_out == conv_out_len(l_in, ktaps, stride, pad), "conv1d_bn_fwd: l_out %d != (l_in+2p-k)/s+1 = %d", l_out,
+                  conv_out_len(l_in, ktaps, stride, pad));
+  DARDS_CHECK_ARG(in_stride >= c_in && y_stride >= c_out && (!out || out_stride >= c_out) && (!res || res_stride >= c_out),
+                  "conv1d_bn_fwd: row stride smaller than channel count");
+  return tc_conv_bn_fwd(in, w_koi, y, out, res, gamma, beta, save_mean, save_rstd, part, n_breaths, group, l_in, l_out, c_in,
+                        c_out, in_stride, y_stride, out_stride, res_stride, ktaps, stride, pad, eps, relu, src_last_use,
+                        S(stream));
+}
+
+int dards_gbn_apply_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta,
+                        const float* part, int entries, float* save_mean, float* save_rstd, const void* x2,
+                        const float* gamma2, const float* beta2, const float* part2, int entries2, float* save_mean2,
+                        float* save_rstd2, int n_groups, int rows_per_group, int c, int x_stride, int out_stride,
+                        int res_stride, int x2_stride, float eps, int relu, int dtype, void* stream) {
+  DARDS_CHECK_ARG(dtype == DARDS_BF16, "gbn_apply_fwd: bf16 only (it follows the fused tcgen05 convolution)");
+  DARDS_CHECK_ARG(x_stride >= c && out_stride >= c, "gbn_apply_fwd: row stride smaller than channel count");
+  return launch_gbn_apply_fwd(x, out, res, gamma, beta, part, entries, save_mean, save_rstd, x2, gamma2, beta2, part2,
+                              entries2, save_mean2, save_rstd2, n_groups, rows_per_group, c, x_stride, out_stride, res_stride,
+                              x2_stride, eps, relu, S(stream));
 }
 
 int dards_gbn_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta, float* save_mean,

@@ -87,6 +87,7 @@ class Plan(object):
                                "fallback" % p0.device)
         self.device = p0.device
         self.simt_only = _conv_impl_override() == "simt" or precision != "bf16"
+        self.fuse_bn = os.environ.get("DEEPARDS_B200_FUSE_BN", "1") != "0"   # A/B switch: conv + BatchNorm in one kernel
         self.bufs = []  # keeps every tensor referenced by a recorded pointer alive
         self.pack = Recorder()
         self.fwd = Recorder()
@@ -243,6 +244,79 @@ class Plan(object):
         self._note_running(bn, mean, rstd, rows, c)
         return mean, rstd
 
+    # ---- convolution + BatchNorm in one kernel (conv_bn_tc.cu) -----------------------------------------------
+    def _cb_shape(self, c, l_in):
+        l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
+        return (self.N, self.group, l_in, l_out, c.cin, c.cout, c.k, c.stride, c.pad)
+
+    def cb_mode(self, c, l_in):
+        """0: separate conv + BatchNorm kernels; 1: statistics in the convolution epilogue + one elementwise pass;
+        2: BatchNorm (+ residual, + ReLU) entirely in the convolution epilogue."""
+        if self.simt_only or not self.fuse_bn or not self._tc_ok(c, "fwd"):
+            return 0
+        return _lib.fn("dards_conv1d_bn_mode")(*self._cb_shape(c, l_in), self.dt)
+
+    def _cb_conv(self, c, bn, src, src_stride, l_in, y, y_stride, out, out_stride, relu, res, res_stride, st, part,
+                 src_last_use):
+        shape = self._cb_shape(c, l_in)
+        mean, rstd = st
+        flags = (1 if relu else 0) | (_lib.HINT_LAST_USE if src_last_use else 0)
+        self.fwd.add("dards_conv1d_bn_fwd", src, c.koi.data_ptr(), y, out, res, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                     mean.data_ptr(), rstd.data_ptr(), part, shape[0], shape[1], shape[2], shape[3], c.cin, c.cout,
+                     src_stride, y_stride, out_stride, res_stride, c.k, c.stride, c.pad, BN_EPS, flags, self.dt)
+
+    def conv_bn_fwd(self, c, bn, src, src_stride, l_in, y, out, relu, res=None, src_last_use=False, ds=None,
+                    part_key="cb_part"):
+        """y = conv(src) and out = [relu](bn(y) [+ res] [+ bn_d(conv_d(src_d))]) with the BatchNorm statistics taken in
+        the convolution epilogue.  `y` / `out` are (N, l_out, cout) plan buffers, `res` a same-shape buffer;
+        ds = (conv record, bn module, source pointer, source stride, source length, y_d buffer): the downsample branch
+        of a ResNet block.  Returns (statistics of bn, statistics of the downsample bn or None).  Both convolutions
+        must report the same mode (cb_mode)."""
+        mode = self.cb_mode(c, l_in)
+        l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
+        cout = c.cout
+        rows = self.group * l_out
+        st = self.stats(cout)
+        std = None
+        res_ptr = res.data_ptr() if res is not None else None
+        if mode == 2:
+            if ds is not None:
+                cd, bnd, dsrc, dstride, dl, yd = ds
+                std = self.stats(cout)
+                resd = self.scratch("ds_res", (self.N, l_out, cout))
+                self._cb_conv(cd, bnd, dsrc, dstride, dl, yd.data_ptr(), cout, resd.data_ptr(), cout, False, None, 0, std,
+                              None, False)
+                self._note_running(bnd, std[0], std[1], rows, cout)
+                res_ptr = resd.data_ptr()
+            self._cb_conv(c, bn, src, src_stride, l_in, y.data_ptr(), cout, out.data_ptr(), cout, relu, res_ptr, cout, st,
+                          None, src_last_use)
+        elif mode == 1:
+            shape = self._cb_shape(c, l_in)
+            entries = _lib.fn("dards_conv1d_bn_part_entries")(*shape)
+            part = self.scratch(part_key, (self.G * entries * 3 * cout,), torch.float32)
+            self._cb_conv(c, bn, src, src_stride, l_in, y.data_ptr(), cout, None, 0, relu, None, 0, st, part.data_ptr(),
+                          src_last_use)
+            x2 = [None, None, None, None, 0, None, None]
+            if ds is not None:
+                cd, bnd, dsrc, dstride, dl, yd = ds
+                std = self.stats(cout)
+                shaped = self._cb_shape(cd, dl)
+                entd = _lib.fn("dards_conv1d_bn_part_entries")(*shaped)
+                partd = self.scratch(part_key + "_d", (self.G * entd * 3 * cout,), torch.float32)
+                self._cb_conv(cd, bnd, dsrc, dstride, dl, yd.data_ptr(), cout, None, 0, False, None, 0, std,
+                              partd.data_ptr(), False)
+                self._note_running(bnd, std[0], std[1], rows, cout)
+                x2 = [yd.data_ptr(), bnd.weight.data_ptr(), bnd.bias.data_ptr(), partd.data_ptr(), entd,
+                      std[0].data_ptr(), std[1].data_ptr()]
+            self.fwd.add("dards_gbn_apply_fwd", y.data_ptr(), out.data_ptr(), res_ptr, bn.weight.data_ptr(),
+                         bn.bias.data_ptr(), part.data_ptr(), entries, st[0].data_ptr(), st[1].data_ptr(), *x2, self.G, rows,
+                         cout, cout, cout, cout if res is not None else 0, cout if ds is not None else 0, BN_EPS,
+                         1 if relu else 0, self.dt)
+        else:
+            raise RuntimeError("conv_bn_fwd called for a shape the fused kernel does not support")
+        self._note_running(bn, st[0], st[1], rows, cout)
+        return st, std
+
     def _note_running(self, bn, mean, rstd, rows, c):
         if self.update_running and getattr(bn, "running_mean", None) is not None:
             self._running.append((mean, rstd, bn, rows, c))
@@ -378,26 +452,40 @@ class Plan(object):
                 cin, cout = c1.cin, c1.cout
                 lo = (L + 2 - 3) // c1.stride + 1
                 y1 = self.new((N, lo, cout))
-                self.conv_fwd(c1, a.data_ptr(), cin, y1.data_ptr(), cout, L)
                 a1 = self.new((N, lo, cout))
-                st1 = self.gbn_fwd(blk.bn1, y1.data_ptr(), cout, a1.data_ptr(), cout, self.group * lo, cout, True)
+                if self.cb_mode(c1, L):
+                    st1, _ = self.conv_bn_fwd(c1, blk.bn1, a.data_ptr(), cin, L, y1, a1, True)
+                else:
+                    self.conv_fwd(c1, a.data_ptr(), cin, y1.data_ptr(), cout, L)
+                    st1 = self.gbn_fwd(blk.bn1, y1.data_ptr(), cout, a1.data_ptr(), cout, self.group * lo, cout, True)
                 y2 = self.new((N, lo, cout))
-                self.conv_fwd(c2, a1.data_ptr(), cout, y2.data_ptr(), cout, lo, src_last_use=True)
                 out = self.new((N, lo, cout))
+                m2 = self.cb_mode(c2, lo)
                 if blk.downsample is not None:
                     cd = self.conv(blk.downsample[0])
                     yd = self.new((N, lo, cout))
-                    self.conv_fwd(cd, a.data_ptr(), cin, yd.data_ptr(), cout, L)
-                    res = self.scratch("ds_res", (N, lo, cout))
-                    std = self.gbn_fwd(blk.downsample[1], yd.data_ptr(), cout, res.data_ptr(), cout, self.group * lo,
-                                       cout, False)
+                    if m2 and self.cb_mode(cd, L) == m2:
+                        st2, std = self.conv_bn_fwd(c2, blk.bn2, a1.data_ptr(), cout, lo, y2, out, True, src_last_use=True,
+                                                    ds=(cd, blk.downsample[1], a.data_ptr(), cin, L, yd))
+                    else:
+                        self.conv_fwd(c2, a1.data_ptr(), cout, y2.data_ptr(), cout, lo, src_last_use=True)
+                        self.conv_fwd(cd, a.data_ptr(), cin, yd.data_ptr(), cout, L)
+                        res = self.scratch("ds_res", (N, lo, cout))
+                        std = self.gbn_fwd(blk.downsample[1], yd.data_ptr(), cout, res.data_ptr(), cout, self.group * lo,
+                                           cout, False)
+                        st2 = self.gbn_fwd(blk.bn2, y2.data_ptr(), cout, out.data_ptr(), cout, self.group * lo, cout, True,
+                                           res=res.data_ptr(), res_stride=cout)
                     r.update(cd=cd, yd=yd, std=std)
                 else:
                     if cin != cout or c1.stride != 1:
                         raise RuntimeError("BasicBlock without downsample must keep the shape")
-                    res = a
-                st2 = self.gbn_fwd(blk.bn2, y2.data_ptr(), cout, out.data_ptr(), cout, self.group * lo, cout, True,
-                                   res=res.data_ptr(), res_stride=cout)
+                    if m2:
+                        st2, _ = self.conv_bn_fwd(c2, blk.bn2, a1.data_ptr(), cout, lo, y2, out, True, res=a,
+                                                  src_last_use=True)
+                    else:
+                        self.conv_fwd(c2, a1.data_ptr(), cout, y2.data_ptr(), cout, lo, src_last_use=True)
+                        st2 = self.gbn_fwd(blk.bn2, y2.data_ptr(), cout, out.data_ptr(), cout, self.group * lo, cout, True,
+                                           res=a.data_ptr(), res_stride=cout)
                 r.update(c1=c1, c2=c2, y1=y1, a1=a1, st1=st1, y2=y2, st2=st2, out=out, lo=lo, cin=cin, cout=cout)
                 self.sites["layer%d.%d.relu1" % (li, bi)] = a1
                 self.sites["layer%d.%d.relu2" % (li, bi)] = out
@@ -478,9 +566,12 @@ class Plan(object):
                 a = self.new((N, L, cin))
                 st1 = self.gbn_fwd(layer.norm1, cat.data_ptr(), ctot, a.data_ptr(), cin, rows, cin, True, x_last_use=False)
                 y1 = self.new((N, L, mid))
-                self.conv_fwd(c1, a.data_ptr(), cin, y1.data_ptr(), mid, L, src_last_use=True)
                 b = self.new((N, L, mid))
-                st2 = self.gbn_fwd(layer.norm2, y1.data_ptr(), mid, b.data_ptr(), mid, rows, mid, True)
+                if self.cb_mode(c1, L):
+                    st2, _ = self.conv_bn_fwd(c1, layer.norm2, a.data_ptr(), cin, L, y1, b, True, src_last_use=True)
+                else:
+                    self.conv_fwd(c1, a.data_ptr(), cin, y1.data_ptr(), mid, L, src_last_use=True)
+                    st2 = self.gbn_fwd(layer.norm2, y1.data_ptr(), mid, b.data_ptr(), mid, rows, mid, True)
                 self.conv_fwd(c2, b.data_ptr(), mid, cat.data_ptr(), ctot, L, dst_ptr_off=cin * esz, src_last_use=True)
                 seed = None
                 drop_p = float(getattr(layer, "drop_rate", 0.0)) if self.dropout else 0.0

@@ -74,6 +74,68 @@ def conv1d_wgrad(x, dout, k, stride, pad, impl=0):
     return dw
 
 
+def conv1d_bn_fwd(x, w, gamma, beta, group, stride, pad, relu, res=None, eps=1e-5, ds=None):
+    """conv -> grouped BatchNorm (+ res) (+ ReLU) through the fused tcgen05 kernel (bf16 only).
+    x (N, L, Cin) channels-last bf16; returns (mode, y, out, mean, rstd, extra).  mode 2: one kernel; mode 1: convolution with
+    statistics partials + the streaming normalisation.  ds = (x_d, w_d, gamma_d, beta_d, stride_d, pad_d): a second
+    convolution + BatchNorm branch added before the ReLU (the downsample branch of a ResNet block; mode 1 only merges
+    it into the same elementwise pass, mode 2 runs it as its own fused call and passes the result as `res`)."""
+    n, l, cin = x.shape
+    cout, _, k = w.shape
+    lo = (l + 2 * pad - k) // stride + 1
+    dev = x.device
+    g = n // group
+    shape = (n, group, l, lo, cin, cout, k, stride, pad)
+    mode = _lib.fn("dards_conv1d_bn_mode")(*shape, _dt(x))
+    if mode == 0:
+        raise RuntimeError("conv1d_bn_fwd: unsupported shape %r" % (shape,))
+    _, koi = pack_conv_weight(w, x.dtype)
+    y = torch.empty((n, lo, cout), dtype=x.dtype, device=dev)
+    out = torch.empty((n, lo, cout), dtype=x.dtype, device=dev)
+    mean = torch.empty((g, cout), dtype=torch.float32, device=dev)
+    rstd = torch.empty((g, cout), dtype=torch.float32, device=dev)
+    extra = {}
+    if ds is not None:
+        xd, wd, gd, bd, sd, pd = ds
+        if mode == 2:
+            _, _, res, md, rd, _ = conv1d_bn_fwd(xd, wd, gd, bd, group, sd, pd, False, eps=eps)
+            extra = dict(mean_d=md, rstd_d=rd)
+            ds = None
+    entries = _lib.fn("dards_conv1d_bn_part_entries")(*shape) if mode == 1 else 0
+    part = torch.empty((max(g * entries * 3 * cout, 1),), dtype=torch.float32, device=dev)
+    _lib.call("dards_conv1d_bn_fwd", x.data_ptr(), koi.data_ptr(), y.data_ptr(), out.data_ptr(),
+              res.data_ptr() if res is not None else None, gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+              rstd.data_ptr(), part.data_ptr(), n, group, l, lo, cin, cout, _rowstride(x), _rowstride(y), _rowstride(out),
+              _rowstride(res) if res is not None else 0, k, stride, pad, eps, 1 if relu else 0, _dt(x), _st(x))
+    if mode == 1:
+        a2 = [None, None, None, None, 0, None, None]
+        x2s = 0
+        if ds is not None:
+            xd, wd, gd, bd, sd, pd = ds
+            nd, ld, cind = xd.shape
+            kd = wd.shape[2]
+            shape_d = (nd, group, ld, lo, cind, cout, kd, sd, pd)
+            if _lib.fn("dards_conv1d_bn_mode")(*shape_d, _dt(x)) != 1:
+                raise RuntimeError("conv1d_bn_fwd: the downsample branch does not run in partial-statistics mode")
+            _, koid = pack_conv_weight(wd, x.dtype)
+            yd = torch.empty((n, lo, cout), dtype=x.dtype, device=dev)
+            ed = _lib.fn("dards_conv1d_bn_part_entries")(*shape_d)
+            partd = torch.empty((g * ed * 3 * cout,), dtype=torch.float32, device=dev)
+            md = torch.empty((g, cout), dtype=torch.float32, device=dev)
+            rd = torch.empty((g, cout), dtype=torch.float32, device=dev)
+            _lib.call("dards_conv1d_bn_fwd", xd.data_ptr(), koid.data_ptr(), yd.data_ptr(), None, None, None, None, None,
+                      None, partd.data_ptr(), n, group, ld, lo, cind, cout, _rowstride(xd), _rowstride(yd), 0, 0, kd, sd, pd,
+                      eps, 0, _dt(x), _st(x))
+            a2 = [yd.data_ptr(), gd.data_ptr(), bd.data_ptr(), partd.data_ptr(), ed, md.data_ptr(), rd.data_ptr()]
+            x2s = _rowstride(yd)
+            extra = dict(mean_d=md, rstd_d=rd, y_d=yd)
+        _lib.call("dards_gbn_apply_fwd", y.data_ptr(), out.data_ptr(), res.data_ptr() if res is not None else None,
+                  gamma.data_ptr(), beta.data_ptr(), part.data_ptr(), entries, mean.data_ptr(), rstd.data_ptr(), *a2, g,
+                  group * lo, cout, _rowstride(y), _rowstride(out), _rowstride(res) if res is not None else 0, x2s, eps,
+                  1 if relu else 0, _dt(x), _st(x))
+    return mode, y, out, mean, rstd, extra
+
+
 def gbn_fwd(x, gamma, beta, group_rows, relu, res=None, eps=1e-5):
     """x (N, L, C); statistics over `group_rows` consecutive rows of the flattened (N*L, C) view."""
     n, l, c = x.shape

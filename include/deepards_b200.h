@@ -104,6 +104,35 @@ int dards_conv1d_wgrad(const void* in, const void* dout, float* dw, int accumula
                        void* stream);
 long long dards_conv1d_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps, int impl);
 
+/* ---- convolution with the BatchNorm that follows it, in one kernel (tcgen05, bf16) -------------- */
+/* conv -> bn -> relu [-> += residual -> relu] (resnet.py:27-38) and conv -> norm -> relu (densenet.py:25-29):
+ * y = conv(in) is stored (the backward needs it); its per-group statistics are taken from the fp32 accumulators in
+ * the convolution epilogue.  dards_conv1d_bn_mode() says what the kernel can do for a shape:
+ *   2  FUSED: a whole group's output fits on chip; the call also writes
+ *        out = [relu](bn(y) [+ res]) and save_mean / save_rstd [n_groups][C]   (no BatchNorm launch at all)
+ *   1  PARTIAL: the call writes y and per-tile moments (count, mean, M2) to `part`
+ *        ([n_groups * entries][3][C] floats, entries = dards_conv1d_bn_part_entries()); dards_gbn_apply_fwd() below
+ *        merges them and does the elementwise normalisation in one streaming pass
+ *   0  unsupported (fp32 storage, or the group does not tile): use dards_conv1d_fwd + dards_gbn_fwd.
+ * `relu` may carry DARDS_HINT_LAST_USE for `in`.  `out`, `res`, gamma ... save_rstd are unused in mode 1, `part` in
+ * mode 2.  n_breaths must be a multiple of `group`. */
+int dards_conv1d_bn_mode(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride,
+                         int pad, int dtype);
+int dards_conv1d_bn_part_entries(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps,
+                                 int stride, int pad);
+int dards_conv1d_bn_fwd(const void* in, const void* w_koi, void* y, void* out, const void* res, const float* gamma,
+                        const float* beta, float* save_mean, float* save_rstd, float* part, int n_breaths, int group,
+                        int l_in, int l_out, int c_in, int c_out, int in_stride, int y_stride, int out_stride,
+                        int res_stride, int ktaps, int stride, int pad, float eps, int relu, int dtype, void* stream);
+/* Mode-1 consumer: out = [relu]( bn(x) [+ res] [+ bn2(x2)] ), statistics merged from `part` (fixed order).  The
+ * optional second normalised operand is the downsample branch of a ResNet block (resnet.py:34-38), so
+ * relu(bn2(conv2(..)) + bn_d(conv_d(x))) is one pass.  Writes save_mean / save_rstd (and the pair of x2). */
+int dards_gbn_apply_fwd(const void* x, void* out, const void* res, const float* gamma, const float* beta,
+                        const float* part, int entries, float* save_mean, float* save_rstd, const void* x2,
+                        const float* gamma2, const float* beta2, const float* part2, int entries2, float* save_mean2,
+                        float* save_rstd2, int n_groups, int rows_per_group, int c, int x_stride, int out_stride,
+                        int res_stride, int x2_stride, float eps, int relu, int dtype, void* stream);
+
 /* ---- grouped BatchNorm1d (+ residual add, + ReLU) ---------------------------------- */
 /* Training-mode nn.BatchNorm1d over groups of `rows_per_group` = group*L rows: biased variance, eps;
  * out = [relu]( (x-mean)*rstd*gamma + beta [+ res] ).  Saves mean/rstd as [n_groups][C] fp32.

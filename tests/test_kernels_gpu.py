@@ -530,3 +530,92 @@ def test_fused_optimizers_match_torch():
         _lib.call("dards_clamp_adam", p.data_ptr(), gr.data_ptr(), ea.data_ptr(), es.data_ptr(), p.numel(), 1e-3, 0.9,
                   0.999, 1e-8, 0.0, 1.0, i + 1, st)
     assert rel_err(p, p_ref.detach()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# convolution + grouped BatchNorm (+ residual) (+ ReLU) in one tcgen05 kernel (conv_bn_tc.cu, bn_apply.cu)
+# ---------------------------------------------------------------------------------------------------------------
+CONV_BN_CASES = [
+    # n, group, cin, cout, l, k, stride, pad, relu, residual, expected mode
+    (40, 20, 64, 64, 56, 3, 1, 1, True, False, 1),      # ResNet layer 1: partial statistics + streaming apply
+    (40, 20, 64, 64, 56, 3, 1, 1, True, True, 1),
+    (40, 20, 64, 128, 56, 3, 2, 1, True, False, 1),     # layer2.0.conv1 (stride 2, per-tap loads)
+    (60, 20, 128, 128, 28, 3, 1, 1, True, True, 1),
+    (40, 20, 128, 256, 28, 3, 2, 1, True, False, 2),    # layer3.0.conv1: the group fits on chip
+    (60, 20, 256, 256, 14, 3, 1, 1, True, True, 2),     # layer 3: fused, 2 sub-tiles, 2 channel tiles
+    (40, 20, 128, 256, 28, 1, 2, 0, False, False, 2),   # layer3 downsample (no ReLU)
+    (40, 20, 256, 512, 14, 3, 2, 1, True, False, 2),
+    (80, 20, 512, 512, 7, 3, 1, 1, True, True, 2),      # layer 4: fused, 1 sub-tile, 4 channel tiles
+    (40, 20, 96, 128, 14, 1, 1, 0, True, False, 2),     # DenseNet conv1 + norm2 (Cin = 96)
+    (40, 20, 64, 128, 56, 1, 1, 0, True, False, 1),     # DenseNet block 1 conv1 + norm2
+    (3000, 20, 512, 512, 7, 3, 1, 1, True, True, 2),    # many jobs per CTA (persistent schedule, park reuse)
+]
+
+
+def _bn_ref(y, gamma, beta, group, eps=1e-5):
+    """y (N, C, L) fp32 -> grouped training-mode BatchNorm (biased variance) + the statistics."""
+    n, c, l = y.shape
+    g = n // group
+    yg = y.view(g, group, c, l)
+    mean = yg.mean(dim=(1, 3))
+    var = yg.var(dim=(1, 3), unbiased=False)
+    rstd = (var + eps).rsqrt()
+    out = (yg - mean[:, None, :, None]) * rstd[:, None, :, None] * gamma[None, None, :, None] + beta[None, None, :, None]
+    return out.view(n, c, l), mean, rstd
+
+
+@pytest.mark.parametrize("case", CONV_BN_CASES)
+def test_conv_bn_tcgen05_fused(case):
+    """y, statistics and the normalised output against torch on the same bf16 operands.  The statistics come from the
+    fp32 accumulators (not from the bf16-rounded y), the normalisation is applied to the stored bf16 y."""
+    n, group, cin, cout, l, k, s, p, relu, has_res, want_mode = case
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(n, cin, l, generator=gen).to(DEV).bfloat16()
+    w = (torch.randn(cout, cin, k, generator=gen) / (cin * k) ** 0.5).to(DEV)
+    gamma = (1.0 + 0.2 * torch.randn(cout, generator=gen)).to(DEV)
+    beta = (0.3 * torch.randn(cout, generator=gen)).to(DEV)
+    lo = (l + 2 * p - k) // s + 1
+    res = torch.randn(n, cout, lo, generator=gen).to(DEV).bfloat16() if has_res else None
+    mode, y, out, mean, rstd, _ = K().conv1d_bn_fwd(cl(x), w, gamma, beta, group, s, p, relu,
+                                                    res=cl(res) if has_res else None)
+    torch.cuda.synchronize()
+    assert mode == want_mode
+    y_ref = F.conv1d(x.float(), w.bfloat16().float(), stride=s, padding=p)
+    assert rel_err(ncl(y).float(), y_ref) < 6e-3          # bf16 rounding of the stored convolution output
+    bn_ref, mean_ref, rstd_ref = _bn_ref(y_ref, gamma, beta, group)
+    assert rel_err(mean, mean_ref) < 2e-5 and rel_err(rstd, rstd_ref) < 2e-5   # fp32 statistics of the fp32 sums
+    # the kernel normalises the bf16-rounded y with those statistics
+    yb = ncl(y).float().view(n // group, group, cout, lo)
+    o_ref = ((yb - mean[:, None, :, None]) * rstd[:, None, :, None] * gamma[None, None, :, None] +
+             beta[None, None, :, None]).view(n, cout, lo)
+    if has_res:
+        o_ref = o_ref + res.float()
+    if relu:
+        o_ref = o_ref.relu()
+    assert rel_err(ncl(out).float(), o_ref) < 6e-3        # one bf16 rounding of the output
+    full = bn_ref + (res.float() if has_res else 0)
+    assert rel_err(ncl(out).float(), full.relu() if relu else full) < 2e-2
+
+
+def test_conv_bn_tcgen05_downsample_branch_merged():
+    """layer2.0 of ResNet-18: out = relu(bn2(conv2(a1)) + bn_d(conv1x1_s2(x))) -- both BatchNorms in ONE elementwise pass."""
+    n, group = 40, 20
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    a1 = torch.randn(n, 128, 28, generator=gen).to(DEV).bfloat16()
+    xin = torch.randn(n, 64, 56, generator=gen).to(DEV).bfloat16()
+    w2 = (torch.randn(128, 128, 3, generator=gen) / 384 ** 0.5).to(DEV)
+    wd = (torch.randn(128, 64, 1, generator=gen) / 8.0).to(DEV)
+    g2, b2 = (1 + 0.1 * torch.randn(128, generator=gen)).to(DEV), (0.1 * torch.randn(128, generator=gen)).to(DEV)
+    gd, bd = (1 + 0.1 * torch.randn(128, generator=gen)).to(DEV), (0.1 * torch.randn(128, generator=gen)).to(DEV)
+    mode, y, out, mean, rstd, ex = K().conv1d_bn_fwd(cl(a1), w2, g2, b2, group, 1, 1, True,
+                                                     ds=(cl(xin), wd, gd, bd, 2, 0))
+    torch.cuda.synchronize()
+    assert mode == 1
+    y2 = F.conv1d(a1.float(), w2.bfloat16().float(), padding=1)
+    yd = F.conv1d(xin.float(), wd.bfloat16().float(), stride=2)
+    o2, m2, r2 = _bn_ref(y2, g2, b2, group)
+    od, md, rd = _bn_ref(yd, gd, bd, group)
+    assert rel_err(mean, m2) < 2e-5 and rel_err(rstd, r2) < 2e-5
+    assert rel_err(ex["mean_d"], md) < 2e-5 and rel_err(ex["rstd_d"], rd) < 2e-5
+    assert rel_err(ncl(ex["y_d"]).float(), yd) < 6e-3
+    assert rel_err(ncl(out).float(), (o2 + od).relu()) < 2e-2

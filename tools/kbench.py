@@ -137,6 +137,61 @@ def stem():
     print("stem bwd: %6.1f us" % timeit(b), flush=True)
 
 
+def convbn():
+    """conv -> BatchNorm (+ residual) -> ReLU: two kernels (conv, gbn_fwd) against the fused path (one kernel where a group
+    fits on chip, else conv with statistics partials + the streaming normalisation)."""
+    from deepards_b200 import kernels as K
+    G = N // GROUP
+    for c, l in SHAPES:
+        rows = GROUP * l
+        xs = [torch.randn(N, l, c, device=DEV).to(BF) for _ in range(ROT)]
+        rs = [torch.randn(N, l, c, device=DEV).to(BF) for _ in range(ROT)]
+        ys = [torch.empty(N, l, c, device=DEV, dtype=BF) for _ in range(ROT)]
+        outs = [torch.empty(N, l, c, device=DEV, dtype=BF) for _ in range(ROT)]
+        w = torch.randn(c, c, 3, device=DEV) * 0.05
+        kio, koi = K.pack_conv_weight(w, BF)
+        gamma, beta = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+        mean, rstd = torch.empty(G, c, device=DEV), torch.empty(G, c, device=DEV)
+        shape = (N, GROUP, l, l, c, c, 3, 1, 1)
+        mode = _lib.fn("dards_conv1d_bn_mode")(*shape, _lib.BF16)
+        entries = _lib.fn("dards_conv1d_bn_part_entries")(*shape) if mode == 1 else 0
+        part = torch.empty(max(G * entries * 3 * c, 1), device=DEV)
+        fl = 2.0 * N * l * c * c * 3
+
+        def two(i, res):
+            k = i % ROT
+            _lib.call("dards_conv1d_fwd", xs[k].data_ptr(), koi.data_ptr(), ys[k].data_ptr(), None, N, l, l, c, c, c, c, 0,
+                      3, 1, 1, _lib.BF16, 1, st())
+            _lib.call("dards_gbn_fwd", ys[k].data_ptr(), outs[k].data_ptr(), rs[k].data_ptr() if res else None,
+                      gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), G, rows, c, c, c, c, 1e-5,
+                      1 | _lib.HINT_LAST_USE, _lib.BF16, st())
+
+        def fused(i, res):
+            k = i % ROT
+            rp = rs[k].data_ptr() if res else None
+            _lib.call("dards_conv1d_bn_fwd", xs[k].data_ptr(), koi.data_ptr(), ys[k].data_ptr(), outs[k].data_ptr(),
+                      rp if mode == 2 else None, gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                      part.data_ptr(), N, GROUP, l, l, c, c, c, c, c, c, 3, 1, 1, 1e-5, 1, _lib.BF16, st())
+            if mode == 1:
+                _lib.call("dards_gbn_apply_fwd", ys[k].data_ptr(), outs[k].data_ptr(), rp, gamma.data_ptr(), beta.data_ptr(),
+                          part.data_ptr(), entries, mean.data_ptr(), rstd.data_ptr(), None, None, None, None, 0, None, None,
+                          G, rows, c, c, c, c, 0, 1e-5, 1, _lib.BF16, st())
+
+        def conv_only(i):
+            k = i % ROT
+            _lib.call("dards_conv1d_bn_fwd", xs[k].data_ptr(), koi.data_ptr(), ys[k].data_ptr(), outs[k].data_ptr(),
+                      None, gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                      part.data_ptr(), N, GROUP, l, l, c, c, c, c, c, c, 3, 1, 1, 1e-5, 1, _lib.BF16, st())
+
+        for res in (False, True):
+            t2 = timeit(lambda i: two(i, res))
+            tf = timeit(lambda i: fused(i, res))
+            print("conv+bn%s C=%3d L=%2d: conv, gbn_fwd %6.1f us | fused (mode %d) %6.1f us  %6.1f TFLOP/s" %
+                  ("+res" if res else "    ", c, l, t2, mode, tf, fl / tf * 1e-6), flush=True)
+        if mode == 1:
+            print("          conv with statistics partials alone: %6.1f us" % timeit(conv_only), flush=True)
+
+
 def copy():
     """the practical floor: torch's elementwise copy / read-only reduction of one 36.7 MB activation tensor, same rotation"""
     for mb, shape in ((36.7, (5120, 56, 64)), (147, (4 * 5120, 56, 64))):
@@ -178,4 +233,4 @@ if __name__ == "__main__":
     if os.environ.get("KBENCH_STAGES"):
         _lib.call("dards_tc_debug_set", 6, int(os.environ["KBENCH_STAGES"]))
     for wname in what:
-        {"bn": bn, "conv": conv, "stem": stem, "bnprof": bnprof, "convprof": convprof, "copy": copy}[wname]()
+        {"bn": bn, "conv": conv, "stem": stem, "bnprof": bnprof, "convprof": convprof, "copy": copy, "convbn": convbn}[wname]()
