@@ -6,8 +6,8 @@
 // conv1x1 -> BatchNorm), so `out = relu(bn2(y2) + bn_d(y_d))` is ONE pass instead of a BatchNorm launch per branch.
 //
 // Every CTA first merges the (count, mean, M2) records that the convolution tiles of its group wrote -- a fixed-order
-// Chan merge, a few dozen loads per channel -- then streams its share of the group's rows: 16-byte vectors, four rows
-// per thread in flight, no shared-memory tile, no second sweep.  HBM traffic = 1 read + 1 write (+ operands).
+// Chan merge, a few dozen loads per channel -- then streams its share of the group's rows: 16-byte vectors, two rows
+// per thread in flight (three CTAs per SM), no shared-memory tile, no second sweep.  HBM traffic = 1 read + 1 write (+ operands).
 #include "common.cuh"
 
 namespace dards {
@@ -48,14 +48,27 @@ __device__ __forceinline__ void apply_unpack8(const uint4& r, float (&v)[8]) {
 __device__ __forceinline__ void merge_moments(const float* __restrict__ part, int entries, int c, int ch, float eps,
                                               float gamma, float beta, float& sc, float& sh, float& mean_o, float& rstd_o) {
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int e = 0; e < entries; ++e) {
-    const float* r = part + (size_t)e * 3 * c + ch;
-    const float ne = r[0], me = r[c], qe = r[2 * c];
-    if (ne > 0.f) {
-      const float nn = n + ne, d = me - mean;
-      mean += d * (ne / nn);
-      m2 += qe + d * d * (n * ne / nn);
-      n = nn;
+  constexpr int ME = 8;   // records fetched together: the loads are independent, the merge is a dependent chain
+  for (int e0 = 0; e0 < entries; e0 += ME) {
+    float ne[ME], me[ME], qe[ME];
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+      ne[u] = 0.f;
+      if (e0 + u < entries) {
+        const float* r = part + (size_t)(e0 + u) * 3 * c + ch;
+        ne[u] = r[0];
+        me[u] = r[c];
+        qe[u] = r[2 * c];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+      if (ne[u] > 0.f) {
+        const float nn = n + ne[u], d = me[u] - mean;
+        mean += d * (ne[u] / nn);
+        m2 += qe[u] + d * d * (n * ne[u] / nn);
+        n = nn;
+      }
     }
   }
   const float var = fmaxf(m2 / fmaxf(n, 1.f), 0.f) + eps;
@@ -67,7 +80,7 @@ __device__ __forceinline__ void merge_moments(const float* __restrict__ part, in
   rstd_o = rstd;
 }
 
-__global__ void __launch_bounds__(256) gbn_apply_fwd_kernel(const GbnApplyArgs a) {
+__global__ void __launch_bounds__(256, 3) gbn_apply_fwd_kernel(const GbnApplyArgs a) {
   extern __shared__ float s_tab[];  // scale[c], shift[c] (, scale2[c], shift2[c])
   const int g = blockIdx.x / a.splits, split = blockIdx.x % a.splits;
   const int c = a.c;
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(256) gbn_apply_fwd_kernel(const GbnApplyArgs a
   const __nv_bfloat16* x2b = a.x2 ? a.x2 + grow * a.x2_stride : nullptr;
   const bool pow2 = (vpr & (vpr - 1)) == 0;
   const int shv = 31 - __clz(vpr);
-  constexpr int U = 4;
+  constexpr int U = 2;
   for (int i0 = threadIdx.x; i0 < n_vec; i0 += 256 * U) {
     uint4 vx[U], vr[U], v2[U];
     int row[U], vec[U];

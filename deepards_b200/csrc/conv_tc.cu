@@ -29,6 +29,15 @@ namespace dards {
 
 int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1, g_dbg_tile_balance = -1;
 int g_dbg_l2_hint = -1;
+extern int g_dbg_cb_pertap, g_dbg_cb_bstages, g_dbg_cb_wide;
+int g_dbg_shared = -1;   // debug key 10: 0 keeps the wide k3/s1 layers on the one-load-per-tap kernel
+
+// conv_bn_tc.cu: k3 / s1 / p1 convolution whose weight tiles are shared by two simultaneously accumulated position tiles
+int tc_conv3_shared(const void* src, const void* wts, void* dst, int n_breaths, int l, int c_red, int c_cols, int src_stride,
+                    int dst_stride, bool reverse_taps, bool accumulate, cudaStream_t st);
+static bool shared_applicable(int l_in, int l_out, int c_red, int ktaps, int stride, int pad) {
+  return g_dbg_shared != 0 && ktaps == 3 && stride == 1 && pad == 1 && l_in == l_out && (c_red > 128 || g_dbg_shared == 2);
+}
 
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
@@ -116,8 +125,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // =========================== TMA producer (whole warp, one elected lane issues: see elect_one) ===========
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = TC_A_BYTES + (uint32_t)n_tile * (TC_BLOCK_K * 2);
@@ -126,11 +136,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int co0 = co_tile * TC_BLOCK_M, n0 = pos_tile * p.nb;
         for (int ti = 0; ti < p.n_taps; ++ti) {
           for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
-            mbar_arrive_expect_tx(full_bar(stage), stage_tx);
-            tma_load_3d(sa, &tm_w, full_bar(stage), kc * TC_BLOCK_K, co0, p.w_tap[ti]);
-            tma_load_4d(sb, &tm_x, full_bar(stage), kc * TC_BLOCK_K, p.in_par[ti], p.in_start[ti], n0);
+            mbar_wait_tight(empty_bar(stage), phase ^ 1u);
+            if (issuer) {
+              const uint32_t sa = smem_base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+              mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+              tma_load_3d(sa, &tm_w, full_bar(stage), kc * TC_BLOCK_K, co0, p.w_tap[ti]);
+              tma_load_4d(sb, &tm_x, full_bar(stage), kc * TC_BLOCK_K, p.in_par[ti], p.in_start[ti], n0);
+            }
             if (++stage == n_stages) {
               stage = 0;
               phase ^= 1u;
@@ -140,41 +152,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
+    // A single warp issues everything and a dependent scalar instruction costs ~5 cycles, so the loop is kept to a
+    // handful of instructions per MMA: 32-bit arithmetic on the descriptors' low words, tight waits, no per-stage
+    // descriptor construction (profiles/r02_mma_issue_probe.txt: the tensor pipe itself sustains 98 % of its rate).
+    {
+      const bool issuer = elect_one();
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
       // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
       // N = the tile's columns rounded up to 16: accumulator column j depends on B row j only, so the surplus columns
       // (rows the TMA never wrote) cannot contaminate the real ones
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(((n_tile + 15) & ~15) >> 3) << 17) |
                              ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+      const uint64_t tmpl = make_sw128_desc(0, desc_lbo16, desc_sbo16, desc_version, 0);
+      const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
+      const uint32_t a_lo0 = (uint32_t)tmpl + (smem_base >> 4);
+      const uint32_t step = TC_STAGE_BYTES >> 4;
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t a_lo = a_lo0, fb = full_bar(0), eb = empty_bar(0);
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(buf), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait_tight(tempty_bar(buf), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_MAX_N;
+        uint32_t acc = 0u;
         for (int ks = 0; ks < k_steps; ++ks) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait_tight(fb, phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
-          const uint64_t a_desc = make_sw128_desc(sa, desc_lbo16, desc_sbo16, desc_version, 0);
-          const uint64_t b_desc = make_sw128_desc(sb, desc_lbo16, desc_sbo16, desc_version, 0);
-#pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+          if (issuer) {
+            const uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+            umma_bf16_lo(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
+            umma_bf16_lo(d_tmem, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+            umma_bf16_lo(d_tmem, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+            umma_bf16_lo(d_tmem, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+            umma_commit(eb);  // frees the smem slot when these MMAs are done
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs are done
+          acc = 1u;
+          a_lo += step; fb += 8; eb += 8;
           if (++stage == n_stages) {
-            stage = 0;
-            phase ^= 1u;
+            stage = 0; phase ^= 1u; a_lo = a_lo0; fb = full_bar(0); eb = empty_bar(0);
           }
         }
-        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+        if (issuer) umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
       }
     }
   } else {
@@ -360,8 +383,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // =========================== TMA producer (whole warp, one elected lane issues) ===========================
+    {
+      const bool issuer = elect_one();
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       const uint32_t b_tx = (uint32_t)(p.nb * lp) * 128u;
@@ -369,17 +393,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int co0 = (tile % p.n_co_tiles) * TC_BLOCK_M, n0 = (tile / p.n_co_tiles) * p.nb;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(emptyb(sb), phb ^ 1u);
-          mbar_arrive_expect_tx(fullb(sb), b_tx);
-          tma_load_4d_pol(b_base + sb * C3_B_BYTES, &tm_x, fullb(sb), kc * TC_BLOCK_K, 0, -1, n0, pol_x);
+          mbar_wait_tight(emptyb(sb), phb ^ 1u);
+          if (issuer) {
+            mbar_arrive_expect_tx(fullb(sb), b_tx);
+            tma_load_4d_pol(b_base + sb * C3_B_BYTES, &tm_x, fullb(sb), kc * TC_BLOCK_K, 0, -1, n0, pol_x);
+          }
           if (++sb == C3_B_STAGES) {
             sb = 0;
             phb ^= 1u;
           }
           for (int t = 0; t < 3; ++t) {
-            mbar_wait(emptya(sa), pha ^ 1u);
-            mbar_arrive_expect_tx(fulla(sa), TC_A_BYTES);
-            tma_load_3d(a_base + sa * TC_A_BYTES, &tm_w, fulla(sa), kc * TC_BLOCK_K, co0, p.w_tap[t]);
+            mbar_wait_tight(emptya(sa), pha ^ 1u);
+            if (issuer) {
+              mbar_arrive_expect_tx(fulla(sa), TC_A_BYTES);
+              tma_load_3d(a_base + sa * TC_A_BYTES, &tm_w, fulla(sa), kc * TC_BLOCK_K, co0, p.w_tap[t]);
+            }
             if (++sa == C3_A_STAGES) {
               sa = 0;
               pha ^= 1u;
@@ -389,47 +417,52 @@ __global__ void __launch_bounds__(C3_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp, one elected lane issues) ===========================
+    {
+      const bool issuer = elect_one();
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_cols >> 3) << 17) |
                              ((uint32_t)(TC_BLOCK_M >> 4) << 24);
       const uint64_t tmpl = make_sw128_desc(0, 1, 1024 >> 4, 1, 0);
+      const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
+      const uint32_t a_lo0 = (uint32_t)tmpl + (a_base >> 4), b_lo0 = (uint32_t)tmpl + (b_base >> 4);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0, fa = fulla(0), ea = emptya(0), fb = fullb(0), eb = emptyb(0);
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        mbar_wait(tempty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        mbar_wait_tight(tempty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_MAX_N;
         uint32_t acc = 0u;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(fullb(sb), phb);
-          const uint64_t b_desc = tmpl + (uint64_t)((b_base + sb * C3_B_BYTES) >> 4);
+          mbar_wait_tight(fb, phb);
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
-            mbar_wait(fulla(sa), pha);
+            mbar_wait_tight(fa, pha);
             tc_fence_after();
-            const uint64_t a_desc = tmpl + (uint64_t)((a_base + sa * TC_A_BYTES) >> 4);
-#pragma unroll
-            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            if (issuer) {
               // tap t: start advanced by t rows (128 B = 8 x 16 B); k: 16 bf16 = 32 B along the swizzle row
-              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(8 * t + 2 * k), idesc, acc);
-              acc = 1u;
+              const uint32_t bt = b_lo + (uint32_t)(8 * t);
+              umma_bf16_lo(d_tmem, a_lo, bt, desc_hi, idesc, acc);
+              umma_bf16_lo(d_tmem, a_lo + 2, bt + 2, desc_hi, idesc, 1u);
+              umma_bf16_lo(d_tmem, a_lo + 4, bt + 4, desc_hi, idesc, 1u);
+              umma_bf16_lo(d_tmem, a_lo + 6, bt + 6, desc_hi, idesc, 1u);
+              umma_commit(ea);
+              if (t == 2) umma_commit(eb);
             }
-            umma_commit(emptya(sa));
+            acc = 1u;
+            a_lo += TC_A_BYTES >> 4; fa += 8; ea += 8;
             if (++sa == C3_A_STAGES) {
-              sa = 0;
-              pha ^= 1u;
+              sa = 0; pha ^= 1u; a_lo = a_lo0; fa = fulla(0); ea = emptya(0);
             }
           }
-          umma_commit(emptyb(sb));
+          b_lo += C3_B_BYTES >> 4; fb += 8; eb += 8;
           if (++sb == C3_B_STAGES) {
-            sb = 0;
-            phb ^= 1u;
+            sb = 0; phb ^= 1u; b_lo = b_lo0; fb = fullb(0); eb = emptyb(0);
           }
         }
-        umma_commit(tfull_bar(buf));
+        if (issuer) umma_commit(tfull_bar(buf));
       }
     }
   } else {
@@ -740,6 +773,10 @@ int tc_conv_fwd(const void* in, const void* w_koi, void* out, const void* addend
     set_error("tcgen05 conv: the addend must be the output itself (in-place accumulation)");
     return DARDS_ERR_UNSUPPORTED;
   }
+  if (shared_applicable(l_in, l_out, c_in, ktaps, stride, pad)) {
+    const int rc = tc_conv3_shared(in, w_koi, out, n_breaths, l_in, c_in, c_out, in_stride, out_stride, false, addend != nullptr, st);
+    if (rc != DARDS_ERR_UNSUPPORTED) return rc;
+  }
   if (tc3_applicable(l_in, c_in, ktaps, stride, pad) && l_in == l_out)
     return tc3_launch(in, w_koi, out, n_breaths, l_in, c_in, c_out, in_stride, out_stride, false, addend != nullptr,
                       src_last_use, st);
@@ -774,6 +811,10 @@ int tc_conv_dgrad(const void* dout, const void* w_kio, void* din, const void* ad
   if (addend != nullptr && (addend != din || addend_stride != din_stride)) {
     set_error("tcgen05 dgrad: the addend must be the output itself (in-place accumulation)");
     return DARDS_ERR_UNSUPPORTED;
+  }
+  if (shared_applicable(l_in, l_out, c_out, ktaps, stride, pad)) {
+    const int rc = tc_conv3_shared(dout, w_kio, din, n_breaths, l_in, c_out, c_in, dout_stride, din_stride, true, addend != nullptr, st);
+    if (rc != DARDS_ERR_UNSUPPORTED) return rc;
   }
   if (tc3_applicable(l_in, c_out, ktaps, stride, pad))
     return tc3_launch(dout, w_kio, din, n_breaths, l_in, c_out, c_in, dout_stride, din_stride, true, addend != nullptr,
@@ -822,6 +863,10 @@ int tc_debug_set(int key, int value) {
   else if (key == 7) g_dbg_wgrad_fuse = value;
   else if (key == 8) g_dbg_tile_balance = value;
   else if (key == 9) g_dbg_l2_hint = value;
+  else if (key == 10) g_dbg_shared = value;
+  else if (key == 11) g_dbg_cb_pertap = value;
+  else if (key == 12) g_dbg_cb_bstages = value;
+  else if (key == 13) g_dbg_cb_wide = value;
   else {
     set_error("tc_debug_set: unknown key %d", key);
     return DARDS_ERR_INVALID_ARGUMENT;

@@ -110,21 +110,25 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
   const int rows = p.nb * p.p_rows;  // rows written by TMA per chunk
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: the whole warp runs the loop, one elected lane issues (tc_common.cuh: elect_one)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)rows * 128u * (uint32_t)(co_chunks + p.n_btiles * ci_chunks);
       const uint64_t pol_b = l2_policy(p.l2_hint != 0);
       for (int it = 0; it < n_iters; ++it) {
         const int n0 = (u_begin + it) * p.nb;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + stage * p.stage_bytes;
-        mbar_arrive_expect_tx(full_bar(stage), tx);
-        for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * WG_CHUNK_A, &tm_a, full_bar(stage), co0 + c * 64, 0, p.a_start, n0);
-        for (int b = 0; b < p.n_btiles; ++b) {
-          const uint32_t sb = sa + p.a_bytes + b * p.b_bytes;
-          for (int c = 0; c < ci_chunks; ++c)
-            tma_load_4d_pol(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0, pol_b);
+        mbar_wait_tight(empty_bar(stage), phase ^ 1u);
+        if (issuer) {
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          mbar_arrive_expect_tx(full_bar(stage), tx);
+          for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * WG_CHUNK_A, &tm_a, full_bar(stage), co0 + c * 64, 0, p.a_start, n0);
+          for (int b = 0; b < p.n_btiles; ++b) {
+            const uint32_t sb = sa + p.a_bytes + b * p.b_bytes;
+            for (int c = 0; c < ci_chunks; ++c)
+              tma_load_4d_pol(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0, pol_b);
+          }
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -133,7 +137,9 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: whole warp, one elected lane issues; all descriptor arithmetic on the 32-bit low words
+    {
+      const bool issuer = elect_one();
       // instruction descriptor: D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = ci_n, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(ci_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -141,8 +147,8 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       uint32_t phase = 0;
       const int k_steps = p.r_pad / 16;
       // Descriptors are built ONCE: everything but the 14-bit start-address field is loop-invariant, and the
-      // start only moves by multiples of 16 bytes, so advancing is a single 64-bit add (the single issuing
-      // thread must spend far fewer than the ~64 cycles an MMA takes on each issue).
+      // start only moves by multiples of 16 bytes, so advancing is a single 32-bit add on the low word (the high words
+      // of the three descriptor kinds differ only in LBO / base offset, which live in the low / high halves as below)
       const uint64_t a_tmpl = make_sw128_desc(0, WG_CHUNK_A >> 4, 1024 >> 4, 1, 0);
       uint64_t b_tmpl[WG_MAX_TAPS];
       uint32_t d_tmem[WG_MAX_TAPS];
@@ -157,45 +163,50 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       // fused taps: N = 192, chunk stride (LBO) = one 128-byte row
       const uint32_t idesc_f = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(192 >> 3) << 17);
       const uint64_t bf_tmpl = make_sw128_desc(0, 128 >> 4, 1024 >> 4, 1, 0) + (uint64_t)(p.a_bytes >> 4);
+      const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), bf_hi = (uint32_t)(bf_tmpl >> 32);
+      const uint32_t b_hi0 = (uint32_t)(b_tmpl[0] >> 32), b_hi1 = (uint32_t)(b_tmpl[1] >> 32), b_hi2 = (uint32_t)(b_tmpl[2] >> 32);
+      const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+      uint32_t s16 = smem_base >> 4, fb = full_bar(0), eb = empty_bar(0);
       for (int it = 0; it < n_iters; ++it) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait_tight(fb, phase);
         tc_fence_after();
-        const uint64_t sa16 = (uint64_t)((smem_base + stage * p.stage_bytes) >> 4);
-        uint64_t a_desc = a_tmpl + sa16;
-        uint64_t b0 = b_tmpl[0] + sa16, b1 = b_tmpl[1] + sa16, b2 = b_tmpl[2] + sa16;
-        uint32_t acc = it != 0 ? 1u : 0u;
-        if (p.fuse_taps) {
-          uint64_t bf = bf_tmpl + sa16;
-#pragma unroll 2
-          for (int kk = 0; kk < k_steps; ++kk) {
-            umma_bf16(d_tmem[0], a_desc, bf, idesc_f, acc);
-            a_desc += 128; bf += 128;
-            acc = 1u;
+        if (issuer) {
+          uint32_t a_lo = (uint32_t)a_tmpl + s16;
+          uint32_t b0 = (uint32_t)b_tmpl[0] + s16, b1 = (uint32_t)b_tmpl[1] + s16, b2 = (uint32_t)b_tmpl[2] + s16;
+          uint32_t acc = it != 0 ? 1u : 0u;
+          if (p.fuse_taps) {
+            uint32_t bf = (uint32_t)bf_tmpl + s16;
+#pragma unroll 4
+            for (int kk = 0; kk < k_steps; ++kk) {
+              umma_bf16_lo2(d_tmem[0], a_lo, a_hi, bf, bf_hi, idesc_f, acc);
+              a_lo += 128; bf += 128;
+              acc = 1u;
+            }
+          } else if (n_taps == 3) {
+#pragma unroll 4
+            for (int kk = 0; kk < k_steps; ++kk) {
+              umma_bf16_lo2(d_tmem[0], a_lo, a_hi, b0, b_hi0, idesc, acc);
+              umma_bf16_lo2(d_tmem[1], a_lo, a_hi, b1, b_hi1, idesc, acc);
+              umma_bf16_lo2(d_tmem[2], a_lo, a_hi, b2, b_hi2, idesc, acc);
+              a_lo += 128; b0 += 128; b1 += 128; b2 += 128;  // 16 reduction rows = 2048 bytes
+              acc = 1u;
+            }
+          } else {
+#pragma unroll 4
+            for (int kk = 0; kk < k_steps; ++kk) {
+              umma_bf16_lo2(d_tmem[0], a_lo, a_hi, b0, b_hi0, idesc, acc);
+              a_lo += 128; b0 += 128;
+              acc = 1u;
+            }
           }
-        } else if (n_taps == 3) {
-#pragma unroll 2
-          for (int kk = 0; kk < k_steps; ++kk) {
-            umma_bf16(d_tmem[0], a_desc, b0, idesc, acc);
-            umma_bf16(d_tmem[1], a_desc, b1, idesc, acc);
-            umma_bf16(d_tmem[2], a_desc, b2, idesc, acc);
-            a_desc += 128; b0 += 128; b1 += 128; b2 += 128;  // 16 reduction rows = 2048 bytes
-            acc = 1u;
-          }
-        } else {
-#pragma unroll 2
-          for (int kk = 0; kk < k_steps; ++kk) {
-            umma_bf16(d_tmem[0], a_desc, b0, idesc, acc);
-            a_desc += 128; b0 += 128;
-            acc = 1u;
-          }
+          umma_commit(eb);
         }
-        umma_commit(empty_bar(stage));
+        s16 += stage16; fb += 8; eb += 8;
         if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
+          stage = 0; phase ^= 1u; s16 = smem_base >> 4; fb = full_bar(0); eb = empty_bar(0);
         }
       }
-      umma_commit(done_bar);
+      if (issuer) umma_commit(done_bar);
     }
   } else {
     // epilogue: partial[split][t][co][ci] (fp32); thread = output channel, 16 input channels per TMEM load

@@ -87,7 +87,9 @@ class Plan(object):
                                "fallback" % p0.device)
         self.device = p0.device
         self.simt_only = _conv_impl_override() == "simt" or precision != "bf16"
-        self.fuse_bn = os.environ.get("DEEPARDS_B200_FUSE_BN", "1") != "0"   # A/B switch: conv + BatchNorm in one kernel
+        # conv + BatchNorm in one kernel: "0" never, "2" only where the whole normalisation runs in the epilogue,
+        # "1" also with statistics partials + the streaming normalisation (long sequences)
+        self.fuse_bn = os.environ.get("DEEPARDS_B200_FUSE_BN", "2")
         self.bufs = []  # keeps every tensor referenced by a recorded pointer alive
         self.pack = Recorder()
         self.fwd = Recorder()
@@ -252,9 +254,10 @@ class Plan(object):
     def cb_mode(self, c, l_in):
         """0: separate conv + BatchNorm kernels; 1: statistics in the convolution epilogue + one elementwise pass;
         2: BatchNorm (+ residual, + ReLU) entirely in the convolution epilogue."""
-        if self.simt_only or not self.fuse_bn or not self._tc_ok(c, "fwd"):
+        if self.simt_only or self.fuse_bn == "0" or not self._tc_ok(c, "fwd"):
             return 0
-        return _lib.fn("dards_conv1d_bn_mode")(*self._cb_shape(c, l_in), self.dt)
+        mode = _lib.fn("dards_conv1d_bn_mode")(*self._cb_shape(c, l_in), self.dt)
+        return 0 if (mode == 1 and self.fuse_bn != "1") else mode
 
     def _cb_conv(self, c, bn, src, src_stride, l_in, y, y_stride, out, out_stride, relu, res, res_stride, st, part,
                  src_last_use):

@@ -548,6 +548,7 @@ CONV_BN_CASES = [
     (80, 20, 512, 512, 7, 3, 1, 1, True, True, 2),      # layer 4: fused, 1 sub-tile, 4 channel tiles
     (40, 20, 96, 128, 14, 1, 1, 0, True, False, 2),     # DenseNet conv1 + norm2 (Cin = 96)
     (40, 20, 64, 128, 56, 1, 1, 0, True, False, 1),     # DenseNet block 1 conv1 + norm2
+    (60, 20, 512, 512, 7, 3, 1, 1, True, True, 2),      # odd number of groups: one group per job
     (3000, 20, 512, 512, 7, 3, 1, 1, True, True, 2),    # many jobs per CTA (persistent schedule, park reuse)
 ]
 
@@ -619,3 +620,26 @@ def test_conv_bn_tcgen05_downsample_branch_merged():
     assert rel_err(ex["mean_d"], md) < 2e-5 and rel_err(ex["rstd_d"], rd) < 2e-5
     assert rel_err(ncl(ex["y_d"]).float(), yd) < 6e-3
     assert rel_err(ncl(out).float(), (o2 + od).relu()) < 2e-2
+
+
+@pytest.mark.parametrize("shape", [(256, 14, 3, 1, 1), (512, 7, 3, 1, 1), (128, 14, 1, 1, 0), (64, 56, 3, 1, 1)])
+def test_conv_bn_tcgen05_is_slice_invariant(shape):
+    """Groups are independent and every reduction has a fixed order: a group's results do not depend on how many other
+    groups the launch holds, which CTA ran it, or which other group shared its job (bit for bit)."""
+    c, l, k, s, p = shape
+    group = 20
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    n_big = 20 * 330                                  # more jobs than SMs: several jobs per CTA
+    x = torch.randn(n_big, l, c, generator=gen).to(DEV).bfloat16()
+    w = (torch.randn(c, c, k, generator=gen) / (c * k) ** 0.5).to(DEV)
+    gamma = (1.0 + 0.2 * torch.randn(c, generator=gen)).to(DEV)
+    beta = (0.3 * torch.randn(c, generator=gen)).to(DEV)
+    _, y, out, mean, rstd, _ = K().conv1d_bn_fwd(x, w, gamma, beta, group, s, p, True)
+    for lo, hi in ((0, 2), (100, 103), (327, 330)):   # even / odd number of groups in the small launch
+        xs = x[lo * group:hi * group].contiguous()
+        _, y2, out2, mean2, rstd2, _ = K().conv1d_bn_fwd(xs, w, gamma, beta, group, s, p, True)
+        torch.cuda.synchronize()
+        assert torch.equal(y[lo * group:hi * group], y2)
+        assert torch.equal(mean[lo:hi], mean2) and torch.equal(rstd[lo:hi], rstd2)
+        assert torch.equal(out[lo * group:hi * group], out2)
+    assert bool(torch.isfinite(out.float()).all())

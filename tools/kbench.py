@@ -230,6 +230,16 @@ if __name__ == "__main__":
         _lib.call("dards_tc_debug_set", 7, int(os.environ["KBENCH_WGRAD_FUSE"]))  # 0: three MMAs per k-step at C=64
     if os.environ.get("KBENCH_TILE_BALANCE"):
         _lib.call("dards_tc_debug_set", 8, int(os.environ["KBENCH_TILE_BALANCE"]))  # 1: wave-balanced tile width
+    if os.environ.get("KBENCH_SHARED"):
+        _lib.call("dards_tc_debug_set", 10, int(os.environ["KBENCH_SHARED"]))  # 0: wide k3/s1 layers on the per-tap kernel; 2: all on the shared-weight loop
+    if os.environ.get("KBENCH_CB_BSTAGES"):
+        _lib.call("dards_tc_debug_set", 12, int(os.environ["KBENCH_CB_BSTAGES"]))
+    if os.environ.get("KBENCH_SHAPES"):
+        SHAPES = [tuple(int(v) for v in sh.split("x")) for sh in os.environ["KBENCH_SHAPES"].split(",")]
+    if os.environ.get("KBENCH_CB_WIDE"):
+        _lib.call("dards_tc_debug_set", 13, int(os.environ["KBENCH_CB_WIDE"]))
+    if os.environ.get("KBENCH_CB_PERTAP"):
+        _lib.call("dards_tc_debug_set", 11, int(os.environ["KBENCH_CB_PERTAP"]))
     if os.environ.get("KBENCH_STAGES"):
         _lib.call("dards_tc_debug_set", 6, int(os.environ["KBENCH_STAGES"]))
     for wname in what:
