@@ -30,13 +30,14 @@ namespace dards {
 int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1, g_dbg_tile_balance = -1;
 int g_dbg_l2_hint = -1;
 extern int g_dbg_cb_pertap, g_dbg_cb_bstages, g_dbg_cb_wide;
-int g_dbg_shared = -1;   // debug key 10: 0 keeps the wide k3/s1 layers on the one-load-per-tap kernel
+int g_dbg_shared = -1;   // debug key 10: 1 routes the wide (> 128 channel) k3/s1 layers through conv_bn_tc.cu's main loop, 2 all of them
 
 // conv_bn_tc.cu: k3 / s1 / p1 convolution whose weight tiles are shared by two simultaneously accumulated position tiles
 int tc_conv3_shared(const void* src, const void* wts, void* dst, int n_breaths, int l, int c_red, int c_cols, int src_stride,
                     int dst_stride, bool reverse_taps, bool accumulate, cudaStream_t st);
 static bool shared_applicable(int l_in, int l_out, int c_red, int ktaps, int stride, int pad) {
-  return g_dbg_shared != 0 && ktaps == 3 && stride == 1 && pad == 1 && l_in == l_out && (c_red > 128 || g_dbg_shared == 2);
+  // opt-in: as fast as the one-load-per-tap kernel in isolation (profiles/r02_kbench_conv_shared.txt), slower inside the step
+  return g_dbg_shared >= 1 && ktaps == 3 && stride == 1 && pad == 1 && l_in == l_out && (c_red > 128 || g_dbg_shared == 2);
 }
 
 constexpr int TC_EPI_WARPS = 8;

@@ -284,7 +284,7 @@ int dards_gradcam(const dards_gradcam_desc* desc /* HOST struct, read during the
 /* ---- debugging ----------------------------------------------------------------------- */
 /* Overrides one field of the tcgen05 shared-memory / instruction descriptors (key: 0 = LBO field,
  * 1 = version field, 2 = SBO field for K-major tiles; 4 = epilogue (0 direct stores, 1 TMA store); 5 = 0 | 1 forces
- * the single-load 3-tap kernel off | on for every k3/s1 layer (default: reductions over <= 128 channels), 6 = 3 pins the operand ring to 3 stages, 7 = 0 issues the 3 wgrad taps of 64-channel layers as 3 MMAs instead of one N = 192 MMA, 8 = 1 opts in to the wave-balanced position-tile width of the wide convolution kernel (measured slower), 9 = 0 loads last-use operands of the backward pass without the L2 evict_first hint, 10 = 0 keeps the wide (> 128 channel) k3/s1 convolutions on the one-load-per-tap kernel instead of the shared-weight-tile main loop of conv_bn_tc.cu, 10 = 2 uses that main loop for every k3/s1 layer; value < 0 restores the default).  Only the unit tests and probes use it. */
+ * the single-load 3-tap kernel off | on for every k3/s1 layer (default: reductions over <= 128 channels), 6 = 3 pins the operand ring to 3 stages, 7 = 0 issues the 3 wgrad taps of 64-channel layers as 3 MMAs instead of one N = 192 MMA, 8 = 1 opts in to the wave-balanced position-tile width of the wide convolution kernel (measured slower), 9 = 0 loads last-use operands of the backward pass without the L2 evict_first hint, 10 = 1 | 2 routes the wide (> 128 channel) | all k3/s1 convolutions through the main loop of conv_bn_tc.cu (plain store epilogue), 11 = 1 makes the fused conv+BatchNorm kernel load the activations once per tap, 12 = its activation-ring depth, 13 = 1 one 256-column tile per job for its plain mode; value < 0 restores the default).  Only the unit tests and probes use it. */
 int dards_tc_debug_set(int key, int value);
 
 #ifdef __cplusplus

@@ -553,7 +553,7 @@ CONV_BN_CASES = [
 ]
 
 
-def _bn_ref(y, gamma, beta, group, eps=1e-5):
+def _bn_group_ref(y, gamma, beta, group, eps=1e-5):
     """y (N, C, L) fp32 -> grouped training-mode BatchNorm (biased variance) + the statistics."""
     n, c, l = y.shape
     g = n // group
@@ -583,7 +583,7 @@ def test_conv_bn_tcgen05_fused(case):
     assert mode == want_mode
     y_ref = F.conv1d(x.float(), w.bfloat16().float(), stride=s, padding=p)
     assert rel_err(ncl(y).float(), y_ref) < 6e-3          # bf16 rounding of the stored convolution output
-    bn_ref, mean_ref, rstd_ref = _bn_ref(y_ref, gamma, beta, group)
+    bn_ref, mean_ref, rstd_ref = _bn_group_ref(y_ref, gamma, beta, group)
     assert rel_err(mean, mean_ref) < 2e-5 and rel_err(rstd, rstd_ref) < 2e-5   # fp32 statistics of the fp32 sums
     # the kernel normalises the bf16-rounded y with those statistics
     yb = ncl(y).float().view(n // group, group, cout, lo)
@@ -614,8 +614,8 @@ def test_conv_bn_tcgen05_downsample_branch_merged():
     assert mode == 1
     y2 = F.conv1d(a1.float(), w2.bfloat16().float(), padding=1)
     yd = F.conv1d(xin.float(), wd.bfloat16().float(), stride=2)
-    o2, m2, r2 = _bn_ref(y2, g2, b2, group)
-    od, md, rd = _bn_ref(yd, gd, bd, group)
+    o2, m2, r2 = _bn_group_ref(y2, g2, b2, group)
+    od, md, rd = _bn_group_ref(yd, gd, bd, group)
     assert rel_err(mean, m2) < 2e-5 and rel_err(rstd, r2) < 2e-5
     assert rel_err(ex["mean_d"], md) < 2e-5 and rel_err(ex["rstd_d"], rd) < 2e-5
     assert rel_err(ncl(ex["y_d"]).float(), yd) < 6e-3
