@@ -44,22 +44,28 @@ namespace dards {
 constexpr int CB_EPI_WARPS = 8;
 constexpr int CB_EPI_THREADS = CB_EPI_WARPS * 32;
 constexpr int CB_THREADS = 64 + CB_EPI_THREADS;
+// FUSED: 8 more warps do the normalisation sweep of job j while the drain warps are on job j + 1
+constexpr int CB_THREADS_FUSED = CB_THREADS + CB_EPI_THREADS;
 constexpr int CB_MAX_A = 8, CB_MAX_B = 8;
 constexpr int CB_A_BYTES = 128 * 64 * 2;   // 16 KB weight tile
 constexpr int CB_MAX_TAPS = 8;
 constexpr int CB_MAX_COLS = 256;
 constexpr int CB_MAX_SUB = 2;
 constexpr int CB_MAX_GPJ = 2;              // groups per job
-// tail of the shared memory: barriers + TMEM slot (512 B) | moments [2 groups][2 halves][4][128] (8 KB) |
-// scale/shift [2 groups][2][128] (2 KB) | column -> row table [256] u16 (512 B)
-constexpr int CB_OFF_MOM = 512, CB_OFF_SCSH = CB_OFF_MOM + 8192, CB_OFF_CROW = CB_OFF_SCSH + 2048,
-              CB_TAIL_BYTES = CB_OFF_CROW + 512;
+// tail of the shared memory: barriers + TMEM slot (512 B) | moments [2 jobs][2 groups][2 halves][4][128] (16 KB) |
+// scale/shift [2 jobs][2 groups][2][128] (4 KB) | column -> element offset table [256] u32 (1 KB) |
+// per-drain-warp transpose scratch [8 warps][16 columns][32 channels] bf16 (8 KB)
+constexpr int CB_OFF_MOM = 512, CB_OFF_SCSH = CB_OFF_MOM + 16384, CB_OFF_CROW = CB_OFF_SCSH + 4096,
+              CB_OFF_TR = CB_OFF_CROW + 1024, CB_TAIL_BYTES = CB_OFF_TR + 8192;
+// named barriers: 2 + par "job's y and moments are ready" (drain warps arrive, apply warps wait), 4 + par "moments consumed"
+// (apply warps arrive, drain warps wait before reusing the slot two jobs later), 6 apply-warp internal
 constexpr int CB_SMEM_LIMIT = 227 * 1024;
 
 enum { CB_PARTIAL = 0, CB_FUSED = 1, CB_PLAIN = 2 };
 int g_dbg_cb_pertap = -1;
 int g_dbg_cb_bstages = -1;
-int g_dbg_cb_wide = -1;     // debug key 13 = 1: plain convolutions use one 256-column tile per job instead of two 160-column ones  // debug key 12: activation-ring depth of the mode3 loop (default 2 chunks)  // debug key 11 = 1: k3/s1 convolutions with BatchNorm use one activation load per tap
+int g_dbg_cb_wide = -1;
+int g_dbg_cb_share = -1;    // debug key 14 = 1: the job's two sub-tiles are accumulated simultaneously (weight tiles fetched once)     // debug key 13 = 1: plain convolutions use one 256-column tile per job instead of two 160-column ones  // debug key 12: activation-ring depth of the mode3 loop (default 2 chunks)  // debug key 11 = 1: k3/s1 convolutions with BatchNorm use one activation load per tap
 
 struct CbParams {
   int mode3;
@@ -73,6 +79,7 @@ struct CbParams {
   int n_bufs;           // TMEM accumulator ring
   int n_pos_jobs, n_co_tiles;
   int a_stages, b_stages, b_bytes;
+  int nshare;           // sub-tiles accumulated simultaneously (1: one after the other)
   int c_out;
   int epi, relu, accumulate;
   int x_evict_first;
@@ -107,8 +114,12 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   return r;
 }
 
-template <int EPI, bool ACC, bool MODE3, int NSUB>
-__global__ void __launch_bounds__(CB_THREADS, 1)
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int EPI, bool ACC, bool MODE3, int NSH>
+__global__ void __launch_bounds__(EPI == CB_FUSED ? CB_THREADS_FUSED : CB_THREADS, 1)
     tc_conv_bn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                       const CbParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -128,8 +139,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(tail + 8 * (2 * CB_MAX_B + 2 * CB_MAX_A + 8));
   float* mom = reinterpret_cast<float*>(tail + CB_OFF_MOM);      // [group][half][cnt, s, ss, shift][128]
   float* scsh = reinterpret_cast<float*>(tail + CB_OFF_SCSH);    // [group][scale, shift][128]
-  // [n_cols]: accumulator column (breath b, position q) -> row b*y_l + q*y_mul of y, 0xFFFF for the junk columns
-  uint16_t* crow = reinterpret_cast<uint16_t*>(tail + CB_OFF_CROW);
+  // [n_cols]: accumulator column (breath b, position q) -> element offset (b*y_l + q*y_mul) * y_stride into y, ~0 for
+  // the junk columns (32-bit: a tile spans at most 256 rows of at most a few thousand elements)
+  uint32_t* crow = reinterpret_cast<uint32_t*>(tail + CB_OFF_CROW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_jobs = p.n_pos_jobs * p.n_co_tiles;
@@ -158,18 +170,18 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
   }
   if (p.mode3) {
     // the zero row after the last breath of every activation stage (TMA never writes it)
-    for (int i = threadIdx.x; i < p.b_stages * 8; i += CB_THREADS) {
+    for (int i = threadIdx.x; i < p.b_stages * 8; i += blockDim.x) {
       uint4* row = reinterpret_cast<uint4*>(smem_gen + (b_base - smem_base) + (i >> 3) * p.b_bytes + p.nb * p.lp * 128);
       row[i & 7] = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async();
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 10) {
     // accumulator column -> output row within the sub-tile, the same for every job
     const int et = threadIdx.x - 64;
     for (int c = et; c < CB_MAX_COLS; c += CB_EPI_THREADS) {
       const int b = c / p.lp, q = c - b * p.lp;
-      crow[c] = (c < p.n_cols && q < p.l && b < p.nb) ? (uint16_t)(b * p.y_l + q * p.y_mul) : (uint16_t)0xFFFFu;
+      crow[c] = (c < p.n_cols && q < p.l && b < p.nb) ? (uint32_t)(b * p.y_l + q * p.y_mul) * (uint32_t)p.y_stride : 0xFFFFFFFFu;
     }
   }
   tc_fence_before();
@@ -198,11 +210,14 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         }
       };
       for (int job = blockIdx.x; job < total_jobs; job += gridDim.x) {
-        const int co0 = (job % p.n_co_tiles) * 128, nj = (job / p.n_co_tiles) * job_breaths;
+        const int co0 = (job % p.n_co_tiles) * 128;
+        // the job's sub-tiles, NSH at a time
+        for (int sg = 0; sg < p.nsub; sg += NSH) {
+        const int nj = (job / p.n_co_tiles) * job_breaths + sg * p.nb;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           if (MODE3) {
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) load_b(kc, 0, -1, nj + sub * p.nb);
+            for (int sub = 0; sub < NSH; ++sub) load_b(kc, 0, -1, nj + sub * p.nb);
           }
           for (int t = 0; t < p.n_taps; ++t) {
             mbar_wait(emptya(sa), pha ^ 1u);
@@ -217,9 +232,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
             }
             if (!MODE3) {
 #pragma unroll
-              for (int sub = 0; sub < NSUB; ++sub) load_b(kc, p.in_par[t], p.in_start[t], nj + sub * p.nb);
+              for (int sub = 0; sub < NSH; ++sub) load_b(kc, p.in_par[t], p.in_start[t], nj + sub * p.nb);
             }
           }
+        }
         }
       }
     }
@@ -244,11 +260,13 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
       uint32_t fa = fulla(0), ea = emptya(0), fb = fullb(0), eb = emptyb(0);
       int buf = 0;        // TMEM ring position of the job's first accumulator
       uint32_t bph = 0;   // its phase
+      const int groups_per_job = p.nsub / NSH;
       for (int job = blockIdx.x; job < total_jobs; job += gridDim.x) {
-        uint32_t d_tmem[NSUB];
-        uint32_t tfull[NSUB];
+      for (int sg = 0; sg < groups_per_job; ++sg) {
+        uint32_t d_tmem[NSH];
+        uint32_t tfull[NSH];
 #pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub) {
+        for (int sub = 0; sub < NSH; ++sub) {
           mbar_wait_tight(tempty_bar(buf), bph ^ 1u);  // the epilogue has drained it
           d_tmem[sub] = tmem_base + (uint32_t)(buf * n_cols);
           tfull[sub] = tfull_bar(buf);
@@ -259,17 +277,17 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         }
         tc_fence_after();
         uint32_t acc = 0u;
-        // both rings hold a multiple of NSUB activation stages (cb_plan), so the NSUB tiles of a chunk / tap are
+        // both rings hold a multiple of NSH activation stages (cb_plan), so the NSH tiles of a chunk / tap are
         // consecutive stages that never wrap in between: one wrap test per group
         for (int kc = 0; kc < k_chunks; ++kc) {
           uint32_t bl0 = 0, eb0 = 0;
           if (MODE3) {
-            // the chunk's NSUB activation tiles stay until its three taps are done
+            // the chunk's NSH activation tiles stay until its three taps are done
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) mbar_wait_tight(fb + 8u * sub, phb);
+            for (int sub = 0; sub < NSH; ++sub) mbar_wait_tight(fb + 8u * sub, phb);
             bl0 = b_lo;
             eb0 = eb;
-            b_lo += NSUB * b_step; fb += 8 * NSUB; eb += 8 * NSUB; sb += NSUB;
+            b_lo += NSH * b_step; fb += 8 * NSH; eb += 8 * NSH; sb += NSH;
             if (sb == b_stages) {
               sb = 0; phb ^= 1u; b_lo = b_lo0; fb = fullb(0); eb = emptyb(0);
             }
@@ -278,12 +296,12 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
             mbar_wait_tight(fa, pha);
             if (!MODE3) {
 #pragma unroll
-              for (int sub = 0; sub < NSUB; ++sub) mbar_wait_tight(fb + 8u * sub, phb);
+              for (int sub = 0; sub < NSH; ++sub) mbar_wait_tight(fb + 8u * sub, phb);
             }
             tc_fence_after();
             if (issuer) {
 #pragma unroll
-              for (int sub = 0; sub < NSUB; ++sub) {
+              for (int sub = 0; sub < NSH; ++sub) {
                 // mode3, tap t: start advanced by t rows of 128 B
                 const uint32_t bt = MODE3 ? bl0 + sub * b_step + (uint32_t)(8 * t) : b_lo + sub * b_step;
                 umma_bf16_lo(d_tmem[sub], a_lo, bt, desc_hi, idesc, acc);
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
             }
             acc = 1u;
             if (!MODE3) {
-              b_lo += NSUB * b_step; fb += 8 * NSUB; eb += 8 * NSUB; sb += NSUB;
+              b_lo += NSH * b_step; fb += 8 * NSH; eb += 8 * NSH; sb += NSH;
               if (sb == b_stages) {
                 sb = 0; phb ^= 1u; b_lo = b_lo0; fb = fullb(0); eb = emptyb(0);
               }
@@ -308,40 +326,43 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
           }
           if (MODE3 && issuer) {
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) umma_commit(eb0 + 8u * sub);
+            for (int sub = 0; sub < NSH; ++sub) umma_commit(eb0 + 8u * sub);
           }
         }
         if (issuer) {
 #pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub) umma_commit(tfull[sub]);
+          for (int sub = 0; sub < NSH; ++sub) umma_commit(tfull[sub]);
         }
         __syncwarp();
       }
+      }
     }
-  } else {
-    // =========================== epilogue (warps 2..9) ===========================
+  } else if (warp < 10) {
+    // =========================== drain warps (2..9): TMEM -> y (global), moments ===========================
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
     const int half = ew >> 2;      // the two warps of a quarter alternate over the 16-column chunks
     const int cl = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;
     const int n_chunks = p.n_cols >> 4;
-    const int sub_rows = p.nb * p.l;
-    const int group_rows = p.spg * sub_rows;
-    const int gpj = p.nsub / p.spg;
+    __nv_bfloat16* tr = reinterpret_cast<__nv_bfloat16*>(tail + CB_OFF_TR) + ew * 512;  // this warp's transpose scratch
     // number of real positions among this thread's columns of one sub-tile
     float cnt_sub = 0.f;
     for (int ch = half; ch < n_chunks; ch += 2)
-      for (int j = 0; j < 16; ++j) cnt_sub += crow[(ch << 4) + j] != 0xFFFFu ? 1.f : 0.f;
+      for (int j = 0; j < 16; ++j) cnt_sub += crow[(ch << 4) + j] != 0xFFFFFFFFu ? 1.f : 0.f;
     int ebuf = 0;        // TMEM ring position, walked exactly like the MMA warp's
     uint32_t ebph = 0;
-    for (int job = blockIdx.x; job < total_jobs; job += gridDim.x) {
+    int jc = 0;          // jobs done by this CTA
+    for (int job = blockIdx.x; job < total_jobs; job += gridDim.x, ++jc) {
       const int pos_job = job / p.n_co_tiles;
       const int co0 = (job % p.n_co_tiles) * 128, nj = pos_job * job_breaths;
       const int co = co0 + cl;
       const bool co_ok = co < p.c_out;
+      const int par = jc & 1;
+      (void)co_ok;
+      // the moments slot of two jobs ago must have been read by the apply warps
+      if (EPI == CB_FUSED && jc >= 2) named_bar_sync(4 + par, 2 * CB_EPI_THREADS);
       float s = 0.f, ss = 0.f, shift = 0.f;
-      for (int sub = 0; sub < NSUB; ++sub) {
+      for (int sub = 0; sub < p.nsub; ++sub) {
         const int buf = ebuf;
         mbar_wait(tfull_bar(buf), ebph);
         if (++ebuf == p.n_bufs) {
@@ -350,41 +371,74 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         }
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.n_cols);
-        // position q of breath n lives at row n*y_l + q*y_mul + y_off of y
-        __nv_bfloat16* ysub = p.y + ((size_t)(nj + sub * p.nb) * p.y_l + p.y_off) * p.y_stride + co;
+        // position q of breath n lives at row n*y_l + q*y_mul + y_off of y.  A chunk (16 columns x this warp's 32
+        // channels) is transposed through 1 KB of shared memory so that a lane stores 16 bytes (8 channels of one
+        // column) instead of 16 times 2 bytes: lane = (column within the pass) * 4 + (group of 8 channels)
+        const int cv = lane & 3, lc = lane >> 2;
+        const int cbase = co0 + quarter * 32 + cv * 8;
+        const bool c_ok = cbase < p.c_out;
+        __nv_bfloat16* ysub = p.y + ((size_t)(nj + sub * p.nb) * p.y_l + p.y_off) * p.y_stride + cbase;
         const bool first = (sub % p.spg) == 0;
         if (first) s = ss = 0.f;
-        for (int ch = half; ch < n_chunks; ch += 2) {
-          uint32_t v[16];
-          tmem_ld16(t_row + (uint32_t)(ch << 4), v);
-          const uint4* cr4 = reinterpret_cast<const uint4*>(crow + (ch << 4));
-          const uint4 r0 = cr4[0], r1 = cr4[1];
-          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          tmem_ld_wait();
+        // software pipeline: the TMEM load of the next chunk is in flight while this one is converted and stored
+        uint32_t va[16], vb[16];
+        tmem_ld16(t_row + (uint32_t)(half << 4), va);
+        auto chunk = [&](int ch, const uint32_t (&v)[16]) {
+          const uint32_t* cr = crow + (ch << 4);
           if (first && ch == half) shift = __uint_as_float(v[0]);  // any sample of the channel's data will do
+          if (EPI != CB_PLAIN) {
+            const uint4* cr4 = reinterpret_cast<const uint4*>(cr);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t r = (j & 1) ? (rw[j >> 1] >> 16) : (rw[j >> 1] & 0xFFFFu);
-            const bool valid = r != 0xFFFFu;  // warp-uniform; written branch-free so that the 16 columns overlap
-            const float x = __uint_as_float(v[j]);
-            if (EPI != CB_PLAIN) {
-              const float d = valid ? x - shift : 0.f;  // a junk column may hold anything, NaN included
-              s += d;
-              ss = fmaf(d, d, ss);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 r4 = cr4[j4];
+              const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                // a junk column may hold anything, NaN included: select, never multiply
+                const float d = rr[jj] != 0xFFFFFFFFu ? __uint_as_float(v[4 * j4 + jj]) - shift : 0.f;
+                s += d;
+                ss = fmaf(d, d, ss);
+              }
             }
-            __nv_bfloat16* dst = ysub + (size_t)r * (size_t)p.y_stride;
-            if (valid && co_ok) {
-              float val = x;
-              if (ACC) val += __bfloat162float(*dst);
-              *dst = __float2bfloat16_rn(val);
+          }
+          __syncwarp();  // the previous chunk's reads of the scratch are done
+#pragma unroll
+          for (int j = 0; j < 16; ++j) tr[j * 32 + lane] = __float2bfloat16_rn(__uint_as_float(v[j]));
+          __syncwarp();
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int col = pass * 8 + lc;
+            const uint32_t r = cr[col];
+            if (r != 0xFFFFFFFFu && c_ok) {
+              uint4 val = *reinterpret_cast<const uint4*>(tr + col * 32 + cv * 8);
+              uint4* dst = reinterpret_cast<uint4*>(ysub + r);
+              if (ACC) {
+                float a[8], b[8];
+                unpack8(val, a);
+                unpack8(*dst, b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += b[k];
+                val = pack8(a);
+              }
+              *dst = val;
             }
+          }
+        };
+        for (int ch = half; ch < n_chunks; ch += 4) {
+          tmem_ld_wait();
+          if (ch + 2 < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 2) << 4), vb);
+          chunk(ch, va);
+          if (ch + 2 < n_chunks) {
+            tmem_ld_wait();
+            if (ch + 4 < n_chunks) tmem_ld16(t_row + (uint32_t)((ch + 4) << 4), va);
+            chunk(ch + 2, vb);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(buf));  // the accumulator may be overwritten
         if (EPI == CB_FUSED && (sub % p.spg) == p.spg - 1) {
-          float* m = mom + ((sub / p.spg) * 2 + half) * 4 * 128 + cl;
+          float* m = mom + (((par * 2 + sub / p.spg) * 2 + half) * 4) * 128 + cl;
           m[0] = cnt_sub * (float)p.spg;
           m[128] = s;
           m[256] = ss;
@@ -400,13 +454,34 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         dst[p.c_out] = shift + s * inv;
         dst[2 * p.c_out] = fmaxf(ss - s * s * inv, 0.f);
       }
-      if (EPI != CB_FUSED) continue;
-      // ---- FUSED: merge the two threads of every channel -> scale / shift; normalise the job's y (an L2 hit) ----
-      named_bar_sync(1, CB_EPI_THREADS);  // moments written; every y store of the job is visible to the CTA
-      if (ew < 4 * gpj) {
-        const int gi = ew >> 2;  // warps 0-3 take group 0, warps 4-7 group 1 (if the job has two)
-        const float* m0 = mom + (gi * 2 + 0) * 4 * 128 + cl;
-        const float* m1 = mom + (gi * 2 + 1) * 4 * 128 + cl;
+      if (EPI == CB_FUSED) {
+        __threadfence_block();                         // y stores and moments before the hand-over
+        named_bar_arrive(2 + par, 2 * CB_EPI_THREADS);  // the apply warps take the job from here
+      }
+    }
+  } else {
+    // =========================== apply warps (10..17, FUSED only): out = relu(y * scale + shift + res) ===============
+    // y of the job was written by this CTA a moment ago: the re-read is an L2 hit, row-wise with 16-byte accesses.
+    const int aw = warp - 10;
+    const int at = threadIdx.x - (64 + CB_EPI_THREADS);
+    const int cl = (aw & 3) * 32 + lane;
+    const int sub_rows = p.nb * p.l;
+    const int group_rows = p.spg * sub_rows;
+    const int gpj = p.nsub / p.spg;
+    const int vec = at & 15, rl = at >> 4;  // 16 vectors of 8 channels x 16 row lanes
+    int jc = 0;
+    for (int job = blockIdx.x; job < total_jobs; job += gridDim.x, ++jc) {
+      const int pos_job = job / p.n_co_tiles;
+      const int co0 = (job % p.n_co_tiles) * 128, nj = pos_job * job_breaths;
+      const int par = jc & 1;
+      named_bar_sync(2 + par, 2 * CB_EPI_THREADS);  // drain warps: y and the moments of this job are complete
+      float* sc_tab = scsh + par * 512;
+      if (aw < 4 * gpj) {
+        // merge the two drain threads of every channel (Chan) -> scale / shift
+        const int gi = aw >> 2;  // warps 0-3 take group 0, warps 4-7 group 1 (if the job has two)
+        const int co = co0 + cl;
+        const float* m0 = mom + (((par * 2 + gi) * 2 + 0) * 4) * 128 + cl;
+        const float* m1 = mom + (((par * 2 + gi) * 2 + 1) * 4) * 128 + cl;
         const float n0 = m0[0], n1 = m1[0];
         const float i0 = n0 > 0.f ? 1.f / n0 : 0.f, i1 = n1 > 0.f ? 1.f / n1 : 0.f;
         const float s0 = m0[128], s1 = m1[128];
@@ -419,72 +494,68 @@ __global__ void __launch_bounds__(CB_THREADS, 1)
         float rstd = rsqrtf(var);
         rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);  // one Newton step: the reference divides by sqrt()
         float sc = 0.f, sh = 0.f;
-        if (co_ok) {
+        if (co < p.c_out) {
           const size_t g = (size_t)pos_job * gpj + gi;
           sc = rstd * p.gamma[co];
           sh = p.beta[co] - mean * sc;
           p.save_mean[g * p.c_out + co] = mean;
           p.save_rstd[g * p.c_out + co] = rstd;
         }
-        scsh[gi * 256 + cl] = sc;
-        scsh[gi * 256 + 128 + cl] = sh;
+        sc_tab[gi * 256 + cl] = sc;
+        sc_tab[gi * 256 + 128 + cl] = sh;
       }
-      named_bar_sync(1, CB_EPI_THREADS);
-      {
-        const int vec = et & 15, rl = et >> 4;  // 16 vectors of 8 channels x 16 row lanes
-        const int c = co0 + vec * 8;
-        if (c < p.c_out) {
-          for (int gi = 0; gi < gpj; ++gi) {
-            float sc[8], sh[8];
+      named_bar_sync(6, CB_EPI_THREADS);                 // scale / shift visible to all apply threads
+      named_bar_arrive(4 + par, 2 * CB_EPI_THREADS);     // the moments slot may be reused
+      const int c = co0 + vec * 8;
+      if (c < p.c_out) {
+        for (int gi = 0; gi < gpj; ++gi) {
+          float sc[8], sh[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              sc[j] = scsh[gi * 256 + vec * 8 + j];
-              sh[j] = scsh[gi * 256 + 128 + vec * 8 + j];
+          for (int j = 0; j < 8; ++j) {
+            sc[j] = sc_tab[gi * 256 + vec * 8 + j];
+            sh[j] = sc_tab[gi * 256 + 128 + vec * 8 + j];
+          }
+          const size_t grow0 = (size_t)nj * p.l + (size_t)gi * group_rows;
+          const __nv_bfloat16* yp = p.y + grow0 * p.y_stride + c;
+          __nv_bfloat16* op = p.out + grow0 * p.out_stride + c;
+          const __nv_bfloat16* rp = p.res ? p.res + grow0 * p.res_stride + c : nullptr;
+          auto one = [&](int row, const uint4& yy, const uint4& rr) {
+            float v[8];
+            unpack8(yy, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            if (rp) {
+              float e[8];
+              unpack8(rr, e);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += e[j];
             }
-            const size_t grow0 = (size_t)nj * p.l + (size_t)gi * group_rows;
-            const __nv_bfloat16* yp = p.y + grow0 * p.y_stride + c;
-            __nv_bfloat16* op = p.out + grow0 * p.out_stride + c;
-            const __nv_bfloat16* rp = p.res ? p.res + grow0 * p.res_stride + c : nullptr;
-            auto one = [&](int row, const uint4& yy, const uint4& rr) {
-              float v[8];
-              unpack8(yy, v);
+            if (p.relu) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-              if (rp) {
-                float e[8];
-                unpack8(rr, e);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += e[j];
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              *reinterpret_cast<uint4*>(op + (size_t)row * p.out_stride) = pack8(v);
-            };
-            const uint4 none = make_uint4(0u, 0u, 0u, 0u);
-            int row = rl;
-            for (; row + 48 < group_rows; row += 64) {  // 4 rows per thread in flight
-              uint4 yy[4], rr[4] = {none, none, none, none};
-#pragma unroll
-              for (int u2 = 0; u2 < 4; ++u2) {
-                yy[u2] = __ldcg(reinterpret_cast<const uint4*>(yp + (size_t)(row + 16 * u2) * p.y_stride));
-                if (rp) rr[u2] = *reinterpret_cast<const uint4*>(rp + (size_t)(row + 16 * u2) * p.res_stride);
-              }
-#pragma unroll
-              for (int u2 = 0; u2 < 4; ++u2) one(row + 16 * u2, yy[u2], rr[u2]);
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            for (; row < group_rows; row += 16) {
-              const uint4 yy = __ldcg(reinterpret_cast<const uint4*>(yp + (size_t)row * p.y_stride));
-              uint4 rr = none;
-              if (rp) rr = *reinterpret_cast<const uint4*>(rp + (size_t)row * p.res_stride);
-              one(row, yy, rr);
+            *reinterpret_cast<uint4*>(op + (size_t)row * p.out_stride) = pack8(v);
+          };
+          const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+          int row = rl;
+          for (; row + 48 < group_rows; row += 64) {  // 4 rows per thread in flight
+            uint4 yy[4], rr[4] = {none, none, none, none};
+#pragma unroll
+            for (int u2 = 0; u2 < 4; ++u2) {
+              yy[u2] = __ldcg(reinterpret_cast<const uint4*>(yp + (size_t)(row + 16 * u2) * p.y_stride));
+              if (rp) rr[u2] = *reinterpret_cast<const uint4*>(rp + (size_t)(row + 16 * u2) * p.res_stride);
             }
+#pragma unroll
+            for (int u2 = 0; u2 < 4; ++u2) one(row + 16 * u2, yy[u2], rr[u2]);
+          }
+          for (; row < group_rows; row += 16) {
+            const uint4 yy = __ldcg(reinterpret_cast<const uint4*>(yp + (size_t)row * p.y_stride));
+            uint4 rr = none;
+            if (rp) rr = *reinterpret_cast<const uint4*>(rp + (size_t)row * p.res_stride);
+            one(row, yy, rr);
           }
         }
       }
-      // `mom` / `scsh` are rewritten by the next job only after every thread has passed its first barrier, which the
-      // slowest thread of this sweep reaches after the sweep: no barrier needed here
     }
   }
 
@@ -565,24 +636,28 @@ static CbPlan cb_plan(int n_breaths, int unit, bool want_bn, int l_out, int c_re
     if (p.n_bufs >= 3 && (n_breaths / nb) % 2 == 0 && min_rings + 4 * p.b_bytes <= budget) p.nsub = 2;
   }
   p.n_pos_jobs = n_breaths / (nb * p.nsub);
+  // Sharing a weight tile between the job's two sub-tiles halves the L2 -> SM weight stream, but both accumulators then
+  // finish together and the next job cannot start before the first is drained; one after the other, the third TMEM
+  // buffer lets the MMAs of the next sub-tile overlap the drain.  The kernel is not L2-bound: default = sequential.
+  p.nshare = (p.nsub == 2 && g_dbg_cb_share == 1) ? 2 : 1;
   int left = budget;
   if (mode3) {
     // activation tiles: two chunks of look-ahead; weight tiles take the rest (a weight tile lasts 4*nsub MMAs)
-    p.b_stages = 2 * p.nsub + (p.nsub == 1 ? 1 : 0);
-    if (g_dbg_cb_bstages > 0) p.b_stages = g_dbg_cb_bstages / p.nsub * p.nsub;
-    while (p.b_stages > 2 * p.nsub && left - p.b_stages * p.b_bytes < 3 * CB_A_BYTES) p.b_stages -= p.nsub;
+    p.b_stages = p.nshare == 2 ? 4 : 3;
+    if (g_dbg_cb_bstages > 0) p.b_stages = g_dbg_cb_bstages / p.nshare * p.nshare;
+    while (p.b_stages > 2 * p.nshare && left - p.b_stages * p.b_bytes < 3 * CB_A_BYTES) p.b_stages -= p.nshare;
     left -= p.b_stages * p.b_bytes;
     p.a_stages = left / CB_A_BYTES;
     if (p.a_stages > CB_MAX_A) p.a_stages = CB_MAX_A;
   } else {
     // per-tap loads consume one weight tile with nsub activation tiles
-    int st = left / (CB_A_BYTES + p.nsub * p.b_bytes);
+    int st = left / (CB_A_BYTES + p.nshare * p.b_bytes);
     if (st > CB_MAX_A) st = CB_MAX_A;
-    if (st * p.nsub > CB_MAX_B) st = CB_MAX_B / p.nsub;
+    if (st * p.nshare > CB_MAX_B) st = CB_MAX_B / p.nshare;
     p.a_stages = st;
-    p.b_stages = st * p.nsub;
+    p.b_stages = st * p.nshare;
   }
-  if (p.a_stages < 2 || p.b_stages < 2 * p.nsub || p.b_stages % p.nsub != 0 || p.b_stages > CB_MAX_B) return w;
+  if (p.a_stages < 2 || p.b_stages < 2 * p.nshare || p.b_stages % p.nshare != 0 || p.b_stages > CB_MAX_B) return w;
   w.smem = p.b_stages * p.b_bytes + p.a_stages * CB_A_BYTES + CB_TAIL_BYTES + 1024;
   w.mode = p.epi == CB_FUSED ? 2 : 1;
   return w;
@@ -659,9 +734,9 @@ static int cb_launch(CbPlan& w, const void* src, const void* wts, int n_breaths,
       }                                                                                                                \
       attr_smem[IDX] = w.smem;                                                                                         \
     }                                                                                                                  \
-    tc_conv_bn_kernel<E, A, M3, NS><<<grid, CB_THREADS, w.smem, st>>>(tm_w, tm_x, p);                                   \
+    tc_conv_bn_kernel<E, A, M3, NS><<<grid, (E) == CB_FUSED ? CB_THREADS_FUSED : CB_THREADS, w.smem, st>>>(tm_w, tm_x, p);                                   \
   } while (0)
-  const bool m3 = p.mode3 != 0, two = p.nsub == 2;
+  const bool m3 = p.mode3 != 0, two = p.nshare == 2;
   if (p.epi == CB_FUSED) {
     if (m3 && two) CB_RUN(0, CB_FUSED, false, true, 2);
     else if (m3) CB_RUN(1, CB_FUSED, false, true, 1);

@@ -29,7 +29,7 @@ namespace dards {
 
 int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1, g_dbg_tile_balance = -1;
 int g_dbg_l2_hint = -1;
-extern int g_dbg_cb_pertap, g_dbg_cb_bstages, g_dbg_cb_wide;
+extern int g_dbg_cb_pertap, g_dbg_cb_bstages, g_dbg_cb_wide, g_dbg_cb_share;
 int g_dbg_shared = -1;   // debug key 10: 1 routes the wide (> 128 channel) k3/s1 layers through conv_bn_tc.cu's main loop, 2 all of them
 
 // conv_bn_tc.cu: k3 / s1 / p1 convolution whose weight tiles are shared by two simultaneously accumulated position tiles
@@ -868,6 +868,7 @@ int tc_debug_set(int key, int value) {
   else if (key == 11) g_dbg_cb_pertap = value;
   else if (key == 12) g_dbg_cb_bstages = value;
   else if (key == 13) g_dbg_cb_wide = value;
+  else if (key == 14) g_dbg_cb_share = value;
   else {
     set_error("tc_debug_set: unknown key %d", key);
     return DARDS_ERR_INVALID_ARGUMENT;

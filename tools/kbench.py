@@ -236,6 +236,8 @@ if __name__ == "__main__":
         _lib.call("dards_tc_debug_set", 12, int(os.environ["KBENCH_CB_BSTAGES"]))
     if os.environ.get("KBENCH_SHAPES"):
         SHAPES = [tuple(int(v) for v in sh.split("x")) for sh in os.environ["KBENCH_SHAPES"].split(",")]
+    if os.environ.get("KBENCH_CB_SHARE"):
+        _lib.call("dards_tc_debug_set", 14, int(os.environ["KBENCH_CB_SHARE"]))
     if os.environ.get("KBENCH_CB_WIDE"):
         _lib.call("dards_tc_debug_set", 13, int(os.environ["KBENCH_CB_WIDE"]))
     if os.environ.get("KBENCH_CB_PERTAP"):
