@@ -62,6 +62,7 @@ _SIGNATURES = {
     "dards_scale_windows": [P, I, P, LL, D, D, I, P],
     "dards_gradcam": [ctypes.POINTER(GradcamDesc), P],
     "dards_tc_debug_set": [I, I],
+    "dards_set_sm_limit": [I],
 }
 _RESTYPES = {"dards_last_error": ctypes.c_char_p, "dards_launch_count": c_longlong, "dards_conv1d_wgrad_workspace_bytes": c_longlong}
 

@@ -57,7 +57,7 @@ class PlanFunction(torch.autograd.Function):
         plan.run_backward()
         g = plan.grads()
         out = [None, None]
-        for i, (_, p) in enumerate(plan.params):
+        for i, p in enumerate(plan.autograd_params()):
             out.append(g.get(id(p)) if ctx.needs_input_grad[2 + i] else None)
         return tuple(out)
 
@@ -74,5 +74,7 @@ def run_plan(net, backbone, linear, x, group, mode, dropout_key=()):
                                   "keep the module in train() mode as train_ards_detector.py does")
     plan = engine.get_plan(net, backbone, linear, n, group, module_precision(net), mode,
                            dropout=dropout_key if training else (), update_running=training)
-    params = [p for _, p in plan.params]
-    return PlanFunction.apply(plan, x, *params)
+    # Only the parameters the backward writes are inputs of the autograd node.  ResNet's conv1_alt / conv2 / bn2 never
+    # take part in forward() (resnet.py:141-163): in the reference they are not in the graph, their hooks never fire and
+    # their .grad stays None -- a None handed to a `p.register_hook(lambda g: g.clamp(...))` hook would raise.
+    return PlanFunction.apply(plan, x, *plan.autograd_params())

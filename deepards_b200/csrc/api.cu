@@ -37,6 +37,7 @@ int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, v
                   int stride, int pad, cudaStream_t st);
 long long tc_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps);
 int tc_debug_set(int key, int value);
+int set_sm_limit(int n);
 int tc_conv_bn_mode(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride, int pad);
 int tc_conv_bn_part_entries(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride,
                             int pad);
@@ -378,5 +379,7 @@ int dards_gradcam(const dards_gradcam_desc* d, void* stream) {
 }
 
 int dards_tc_debug_set(int key, int value) { return tc_debug_set(key, value); }
+
+int dards_set_sm_limit(int n_sms) { return set_sm_limit(n_sms); }
 
 }  // extern "C"

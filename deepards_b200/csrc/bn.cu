@@ -736,15 +736,8 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
 // ---- host launchers ------------------------------------------------------------------------------
 static int vec_of(int dtype) { return dtype == DARDS_BF16 ? 8 : 4; }
 
-static int bn_sm_count() {
-  static int n = 0;
-  if (n) return n;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  if (n <= 0) n = 148;
-  return n;
-}
+int sm_count();  // conv_tc.cu: device SM count, or the limit set by dards_set_sm_limit
+static int bn_sm_count() { return sm_count(); }
 
 // cached-kernel configurations: (threads, vectors per row) in order of preference for a given row count
 struct BnCfg { int threads, vpr; };

@@ -556,14 +556,23 @@ int make_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
   return DARDS_OK;
 }
 
+// SMs the persistent kernels size their grids for.  dards_set_sm_limit(n) (data-parallel runs) leaves a few SMs to the
+// NCCL kernels that overlap the backward pass: a persistent kernel launched with one CTA per SM while NCCL holds some of
+// them runs its last CTAs as a second wave.
+static int g_sm_limit = 0;
 int sm_count() {
   static int n = 0;
-  if (n) return n;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  if (n <= 0) n = 148;
-  return n;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+int set_sm_limit(int n) {
+  g_sm_limit = n > 0 ? n : 0;
+  return DARDS_OK;
 }
 
 // breaths per position tile: the largest nb with nb*l <= 256 and (nb*l) % 16 == 0

@@ -16,6 +16,8 @@ notes is effectively unusable (:198-203).  Semantics kept from that path (SURVEY
 The gradient buffer is reduced in buckets, last layers first, on a communication stream that waits on events
 recorded inside the backward pass, so the reduction of layer4's 11.5 MB overlaps the backward of layers 1-3.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -102,6 +104,12 @@ class BucketedAllReduce(object):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self.handles.append(dist.all_reduce(flat[begin:end], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def reduce_now(self, flat, begin, end):
+        """All-reduce ordered on the CURRENT stream: work issued to it afterwards (the bucket's optimizer update) sees the
+        reduced values; the host does not block."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(flat[begin:end], op=dist.ReduceOp.SUM, group=self.group)
+
     def wait(self):
         for h in self.handles:
             h.wait()
@@ -110,7 +118,7 @@ class BucketedAllReduce(object):
 
 class DataParallelTrainer(object):
     def __init__(self, net, lr=1e-3, optimizer="sgd", momentum=0.9, weight_decay=1e-4, clip_val=0.01, group=None,
-                 bucket_mb=4.0, use_graph=False):
+                 bucket_mb=1.0, use_graph=False):
         if optimizer not in ("sgd", "adam"):
             raise ValueError("optimizer must be 'sgd' or 'adam'")
         self.use_graph = use_graph
@@ -119,7 +127,6 @@ class DataParallelTrainer(object):
         # (issued on the communication stream, which joins the capture through the same events that order it in eager
         # mode) in one CUDA graph: measured no faster at 2 GPUs (164.6 k vs ~165 k seq/s) and the processes hang in
         # destroy_process_group() at exit with torch 2.11 / NCCL 2.28, so it is not the default.
-        import os
         self.dp_graph = os.environ.get("DEEPARDS_B200_DP_GRAPH", "segments")
         self.graph_launches = 0  # kernels launched through CUDA-graph replays (not seen by dards_launch_count)
         self.net, self.lr, self.optimizer = net, lr, optimizer
@@ -133,6 +140,13 @@ class DataParallelTrainer(object):
         self._flatten()
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self.reducer = BucketedAllReduce(group)
+        if self.world > 1:
+            # Leave a few SMs to the NCCL kernels that run next to the backward pass: every persistent kernel here launches
+            # one CTA per SM, and with some SMs held by NCCL its last CTAs would run as a second wave.
+            reserve = int(os.environ.get("DEEPARDS_B200_DP_SM_RESERVE", "8"))
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            if 0 < reserve < sms:
+                _lib.call("dards_set_sm_limit", sms - reserve)
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     # ---- flat parameter / optimizer-state buffers (same slot table as Plan.grad_flat) ----------------------
@@ -221,10 +235,12 @@ class DataParallelTrainer(object):
         _lib.call("dards_bce_with_logits", plan.logits.data_ptr(), t_static.data_ptr(), self.loss_buf.data_ptr(),
                   plan.dlogits.data_ptr(), plan.logits.numel(), plan.__dict__.get("_dp_grad_scale", 1.0), st)
         if self.world > 1:
-            self._backward_overlapped(plan)
+            self.step_count += 1
+            self._backward_overlapped(plan)   # all-reduce + optimizer per bucket, on the communication stream
+            plan._packed_version = None
         else:
             plan.run_backward()
-        self._update(plan, st)
+            self._update(plan, st)
 
     def _graphed_step(self, plan, t_static):
         """The SGD step as ONE CUDA-graph launch (weight packing, forward, loss, backward, update: ~200 kernel
@@ -273,32 +289,27 @@ class DataParallelTrainer(object):
             st["graphs"] = self._capture_segments(plan, t_static)
         g = st["graphs"]
         cur = torch.cuda.current_stream(self.device)
+        if self.step_count > 0:
+            cur.wait_stream(self.comm_stream)   # the previous step's last parameter updates ran on the communication stream
+        self.step_count += 1
         g["fwd"].replay()
         plan.fwd_serial += 1
         pending = list(plan._dp_buckets)
         for seg_graph, done_from in g["bwd"]:
             seg_graph.replay()
-            if done_from is not None and pending and pending[0][0] >= done_from:
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                self.comm_stream.wait_event(ev)
-                with torch.cuda.stream(self.comm_stream):
-                    while pending and pending[0][0] >= done_from:
-                        b, e = pending.pop(0)
-                        self.reducer.reduce(plan.grad_flat, b, e)
+            ready = []
+            while done_from is not None and pending and pending[0][0] >= done_from:
+                ready.append(pending.pop(0))
+            if ready:
+                self._reduce_and_update(plan, ready, cur)
         if pending:
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self.comm_stream.wait_event(ev)
-            with torch.cuda.stream(self.comm_stream):
-                for b, e in pending:
-                    self.reducer.reduce(plan.grad_flat, b, e)
+            self._reduce_and_update(plan, pending, cur)
         plan.bwd_serial = plan.fwd_serial
-        self.reducer.wait()
-        cur.wait_stream(self.comm_stream)
-        g["upd"].replay()
-        self.step_count += 1
+        plan._packed_version = None
         self.graph_launches += g["launches"]
+        # the loss is read by the caller on the current stream: nothing of this step is left on it but the backward; the
+        # next step (or a reader of the parameters) waits for the communication stream
+        cur.wait_stream(self.comm_stream)
         return self.loss_buf
 
     def _capture_segments(self, plan, t_static):
@@ -345,17 +356,15 @@ class DataParallelTrainer(object):
             out["bwd"].append((capture(run_seg), off))
             begin = idx
 
-        def upd():
-            self._update(plan, plan._stream())
-            self.step_count -= 1  # capture does not execute; the replay loop counts the step
-
-        out["upd"] = capture(upd)
-        out["launches"] = int(lib.dards_launch_count() - l0)
+        # launches per replayed step: the captured kernels + the per-bucket optimizer launches issued behind the all-reduces
+        n_upd = sum(1 for lo, hi in plan._dp_buckets for b, e in plan._dp_ranges if max(b, lo) < min(e, hi))
+        out["launches"] = int(lib.dards_launch_count() - l0) + n_upd
         return out
 
     def _backward_overlapped(self, plan):
         """Replay the backward in segments; after each segment the comm stream reduces the buckets that became
-        complete.  Buckets are suffixes of the flat buffer (backward finishes the last layers first)."""
+        complete and updates their parameters.  Buckets are suffixes of the flat buffer (backward finishes the last
+        layers first)."""
         if plan.bwd_serial == plan.fwd_serial:
             raise RuntimeError("backward() without a new forward()")
         cur = torch.cuda.current_stream(self.device)
@@ -368,24 +377,52 @@ class DataParallelTrainer(object):
             if rc != 0:
                 _lib.check(rc, name)
             done_from = marks.get(i + 1)
-            if done_from is not None and pending and pending[0][0] >= done_from:
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                self.comm_stream.wait_event(ev)
-                with torch.cuda.stream(self.comm_stream):
-                    while pending and pending[0][0] >= done_from:
-                        b, e = pending.pop(0)
-                        self.reducer.reduce(plan.grad_flat, b, e)
+            ready = []
+            while done_from is not None and pending and pending[0][0] >= done_from:
+                ready.append(pending.pop(0))
+            if ready:
+                self._reduce_and_update(plan, ready, cur)
         if pending:
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self.comm_stream.wait_event(ev)
-            with torch.cuda.stream(self.comm_stream):
-                for b, e in pending:
-                    self.reducer.reduce(plan.grad_flat, b, e)
+            self._reduce_and_update(plan, pending, cur)
         plan.bwd_serial = plan.fwd_serial
-        self.reducer.wait()
         cur.wait_stream(self.comm_stream)
+
+    def _update_bucket(self, plan, lo, hi, st):
+        """The optimizer step for the live parameter ranges inside the flat slice [lo, hi) -- issued right behind that
+        bucket's all-reduce on the communication stream, so only the LAST (small) bucket's update is on the step's tail."""
+        for b, e in plan._dp_ranges:
+            b, e = max(b, lo), min(e, hi)
+            if b < e:
+                self._update_range(plan, b, e, st)
+
+    def _update_range(self, plan, b, e, st):
+        scale = 1.0 / self.world
+        g, p = plan.grad_flat.data_ptr(), self.param_flat.data_ptr()
+        if self.optimizer == "sgd":
+            _lib.call("dards_clamp_sgd_nesterov", p + 4 * b, g + 4 * b, self.state1.data_ptr() + 4 * b, e - b, self.lr,
+                      self.momentum, self.weight_decay, self.clip, scale, 1 if self.step_count == 1 else 0, st)
+        else:
+            _lib.call("dards_clamp_adam", p + 4 * b, g + 4 * b, self.state1.data_ptr() + 4 * b,
+                      self.state2.data_ptr() + 4 * b, e - b, self.lr, 0.9, 0.999, 1e-8, self.clip, scale,
+                      self.step_count, st)
+
+    def _reduce_and_update(self, plan, buckets, cur):
+        """comm stream: wait for the backward work recorded so far, all-reduce the given buckets, update their parameters."""
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            for b, e in buckets:
+                self.reducer.reduce_now(plan.grad_flat, b, e)
+                self._update_bucket(plan, b, e, self.comm_stream.cuda_stream)
+
+    def close(self):
+        """Drop the captured CUDA graphs (they hold NCCL work when the whole step is captured: destroy them before
+        torch.distributed.destroy_process_group())."""
+        torch.cuda.synchronize(self.device)
+        for plan in list(getattr(self.net, "_dards_plans", {}).values()):
+            plan.__dict__.pop("_dp_graph", None)
+            plan.__dict__.pop("_dp_seg", None)
 
     def _update(self, plan, st):
         self.step_count += 1

@@ -27,8 +27,9 @@ SEQ_LEN = 224
 
 _DTYPES = {"fp32": (torch.float32, _lib.F32), "bf16": (torch.bfloat16, _lib.BF16)}
 
-# Smallest gradient suffix (fp32 elements) worth an all-reduce bucket of its own: 4 MB, the trainer's default bucket size.
-DP_MARK_ELEMS = int(os.environ.get("DEEPARDS_B200_DP_BUCKET_ELEMS", 1 << 20))
+# Smallest gradient suffix (fp32 elements) worth an all-reduce bucket of its own: 1 MB, the trainer's default bucket size.
+# ResNet-18: layer4.1 | layer4.0 | layer3.1 | layer3.0 | the rest (1.2 MB: the only all-reduce + update on the step's tail).
+DP_MARK_ELEMS = int(os.environ.get("DEEPARDS_B200_DP_BUCKET_ELEMS", 1 << 18))
 
 
 def _multi_rank():
@@ -735,6 +736,10 @@ class Plan(object):
     def mark_no_backward(self):
         """forward-only use (no_grad): keep the serial numbers consistent."""
         self.bwd_serial = self.fwd_serial
+
+    def autograd_params(self):
+        """The parameters that receive a gradient from this plan's backward, in named_parameters() order."""
+        return [p for _, p in self.params if id(p) in self.grad_written]
 
     def grads(self):
         """{param: gradient view} for every parameter the backward writes (fresh copy of the flat buffer)."""

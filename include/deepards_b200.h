@@ -57,6 +57,11 @@ long long dards_launch_count(void);
 /* 1 if the device behind the current context is compute capability 10.x (B200). */
 int dards_device_supported(void);
 
+/* Persistent kernels launch one CTA per SM.  n_sms > 0 makes them size their grids for n_sms SMs instead (0 restores
+ * the device count): a data-parallel run leaves a few SMs to the NCCL kernels that overlap the backward pass, otherwise
+ * every persistent kernel that meets them runs its last CTAs as a second wave. */
+int dards_set_sm_limit(int n_sms);
+
 /* ---- weights ---------------------------------------------------------------------- */
 /* nn.Conv1d weight (Cout, Cin, K) fp32 [resnet.py:7,88,128; densenet.py:25,30,75,119] ->
  * the two packed forms the kernels read, in `dtype`:

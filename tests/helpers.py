@@ -17,6 +17,8 @@ CASES = {
                                 dict(first_pool_type="avg"), False),
     "densenet18_B2_real": (dict(backbone="densenet18", seed=4, bn_perturb=0.1), {}, False),
     "densenet18_B3_synth": (dict(backbone="densenet18", seed=5, bn_perturb=0.1), {}, False),
+    # all 20 real sequences of the reference's tests/test_dataset.pkl (oracle/make_golden_real20.py)
+    "densenet18_B20_real_all": (dict(backbone="densenet18", seed=7, bn_perturb=0.1), {}, False),
     "resnet18_p16_B2_perbreath": (dict(backbone="resnet18", seed=6, bn_perturb=0.1, initial_planes=16, per_breath=True),
                                   {}, True),
 }

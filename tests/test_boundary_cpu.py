@@ -257,9 +257,10 @@ def test_sibling_heads_gradcam_and_scaler_boundary_on_cpu():
 
 def test_data_parallel_marks_are_bucket_sized():
     """engine.Plan.mark: a mark (= a partial-sum reduction launch + a graph boundary in the multi-GPU step) only where
-    at least one 4 MB bucket of gradients has become final; the trainer's buckets are cut at marks only."""
+    at least one 1 MB bucket of gradients has become final; the trainer's buckets are cut at marks only.  The LAST bucket
+    (all-reduce + optimizer update on the step's tail, nothing left to overlap them with) stays small."""
     from deepards_b200 import data_parallel as dp, engine
-    assert engine.DP_MARK_ELEMS == 1 << 20
+    assert engine.DP_MARK_ELEMS == 1 << 18
     # ResNet-18 slot offsets of the first parameter of each block, last block first (3.89 M elements in total)
     total = 3_893_378
     offs = [2_318_000, 1_006_000, 612_000, 283_000, 185_000, 103_000, 78_000, 53_000]
@@ -268,6 +269,22 @@ def test_data_parallel_marks_are_bucket_sized():
         if last - off >= engine.DP_MARK_ELEMS:
             marks.append(off)
             last = off
-    assert marks == [2_318_000, 1_006_000]
-    assert dp.make_buckets(total, marks, 1 << 20) == [(2_318_000, total), (1_006_000, 2_318_000), (0, 1_006_000)]
-    assert dp.make_buckets(214_850, [], 1 << 20) == [(0, 214_850)]          # DenseNet-18: one bucket
+    assert marks == [2_318_000, 1_006_000, 612_000, 283_000]
+    assert dp.make_buckets(total, marks, 1 << 18) == [(2_318_000, total), (1_006_000, 2_318_000), (612_000, 1_006_000),
+                                                      (283_000, 612_000), (0, 283_000)]
+    assert dp.make_buckets(214_850, [], 1 << 18) == [(0, 214_850)]          # DenseNet-18: one bucket
+
+
+def test_benchmark_workload_generator_equals_the_oracles():
+    """bench.py's product arm takes its synthetic batches from deepards_b200.synthetic (so that it imports nothing from
+    oracle/); the oracle's own generator, used by the parity tests, must produce the same tensors bit for bit."""
+    import torch
+    from deepards_b200 import synthetic as S
+    from oracle import cnn_linear_oracle as O
+    for seed in (1234, 77):
+        assert torch.equal(S.synthetic_breaths(3, seed=seed), O.synthetic_breaths(3, seed=seed))
+        assert torch.equal(S.synthetic_targets(5, seed=seed), O.synthetic_targets(5, seed=seed))
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    b200_arm = src[src.index("def run_b200"):src.index("def kernel_roofline")]
+    # the only oracle use inside the product arm is the cpu_baseline leg (cpu_reference_steps), never an import
+    assert "from oracle" not in b200_arm and "import oracle" not in b200_arm

@@ -23,10 +23,10 @@ from tests.helpers import (CASES, cosine, golden_grad_errors, load_case, pinned_
 FP32_TOL = 1e-4          # north_star: logits and gradients within 1e-4 relative error in fp32
 # bf16 storage + tcgen05 path (the "separately stated, looser tolerance" of the north_star).  bf16 rounding (2^-9)
 # of every stored activation flips ~0.3 % of the ReLU decisions, so gradients are compared by direction:
-BF16_LOGIT_TOL = 1e-1    # logits, max-abs relative (measured 2e-2 .. 5e-2)
-BF16_LOSS_TOL = 2e-2     # absolute, loss ~0.7
-BF16_GRAD_COS = 0.80     # every parameter-gradient tensor with >= 64 elements (measured min 0.84)
-BF16_GRAD_COS_MEAN = 0.93  # mean over those tensors (measured 0.95 .. 0.97)
+BF16_LOGIT_TOL = 8e-2    # logits, max-abs relative (measured 2.0e-2 ResNet-18, 5.0e-2 DenseNet-18)
+BF16_LOSS_TOL = 5e-3     # absolute, loss ~0.7 (measured < 1e-3)
+BF16_GRAD_COS = 0.82     # every parameter-gradient tensor with >= 64 elements (measured min 0.907 / 0.898)
+BF16_GRAD_COS_MEAN = 0.93  # mean over those tensors (measured 0.955 / 0.951)
 
 
 def build(name_or_kw, sd, precision="fp32", per_breath=False, fkw=None):
@@ -261,3 +261,125 @@ def test_dropout_training_mode_is_stochastic_but_eval_like_when_off():
         c, d = net(x, None), net(x, None)
         assert torch.equal(c, d)
         assert rel_err(c.cpu(), O.cnn_linear_forward(sd, x.cpu())) <= FP32_TOL  # BN still uses batch stats
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 path where the headline lives: the benchmarked batch size, and a training trajectory
+# ---------------------------------------------------------------------------------------------------------------
+# Gates = about twice the values measured on the B200 (tests/golden/parity_report_r02.txt).  At B = 256 a parameter
+# gradient is a sum over 256 sequences, so the bf16 rounding noise averages out and the directions agree better than at
+# B = 8.
+# measured (profiles/r02_parity_report.txt): ResNet-18 logits 1.9e-2, |dloss| 1e-4, cosine min 0.896 (stem conv) / mean 0.951
+# / all gradients as one vector 0.994; DenseNet-18 3.0e-2, 2e-5, 0.560 (stem conv: 448 numbers whose 256-sequence mean nearly
+# cancels with random targets, so what is left is mostly rounding; 0.87 with another seed) / 0.938 / 0.753.  The fp32
+# reference itself is only good to 5e-3 on these gradients (oracle fp32 vs fp64, tools/parity_report.py), and the
+# trajectory test below shows that 200 optimizer steps follow the fp32 run to 1e-2 in the loss.
+BF16_B256 = {
+    "resnet18": dict(logit=4e-2, loss=1e-3, cos_min=0.80, cos_mean=0.90, cos_all=0.93),
+    "densenet18": dict(logit=6e-2, loss=1e-3, cos_min=0.40, cos_mean=0.88, cos_all=0.60),
+}
+
+
+@pytest.mark.parametrize("backbone", ["resnet18", "densenet18"])
+def test_bf16_step_at_the_benchmarked_batch_size_vs_oracle(backbone):
+    """BASELINE.json configs[1] / [2] size: one bf16 training step on 256 x 20 x 1 x 224 against the fp32 CPU oracle
+    (logits, loss, every parameter gradient by direction).  wgrad's split-K count and the tile schedules depend on the
+    batch, so this is the configuration bench.py times."""
+    B = 256
+    skw = dict(backbone=backbone, seed=23, bn_perturb=0.1)
+    sd = O.cnn_linear_state(**skw)
+    x = O.synthetic_breaths(B, seed=105)
+    t = O.synthetic_targets(B, seed=105)
+    torch.set_num_threads(max(1, (torch.get_num_threads())))
+    ref_out, ref_loss, ref_grads = O.forward_backward(sd, x, t)
+    net = build(skw, sd, "bf16")
+    out, loss, grads = step(net, x, t)
+    g = BF16_B256[backbone]
+    e_logit = rel_err(out, ref_out)
+    cs = {k: cosine(grads[k].cpu(), v) for k, v in ref_grads.items() if v.numel() >= 64}
+    worst = min(cs, key=cs.get)
+    mean = sum(cs.values()) / len(cs)
+    keys = [k for k in ref_grads]
+    c_all = cosine(torch.cat([grads[k].cpu().reshape(-1) for k in keys]), torch.cat([ref_grads[k].reshape(-1) for k in keys]))
+    print("%s bf16 B=256: logits rel err %.3e, |dloss| %.3e, grad cosine min %.4f (%s) mean %.4f over %d tensors, all "
+          "gradients as one vector %.4f" % (backbone, e_logit, abs(loss - float(ref_loss)), cs[worst], worst, mean, len(cs), c_all))
+    assert c_all >= g["cos_all"], c_all
+    assert e_logit <= g["logit"], e_logit
+    assert abs(loss - float(ref_loss)) <= g["loss"]
+    assert cs[worst] >= g["cos_min"], (worst, cs[worst])
+    assert mean >= g["cos_mean"], mean
+
+
+@pytest.mark.parametrize("backbone", ["resnet18", "densenet18"])
+def test_bf16_training_trajectory_tracks_the_fp32_oracle(backbone):
+    """200 steps of the reference's optimizer (clamp 0.01 + SGD lr 1e-3 momentum 0.9 nesterov wd 1e-4,
+    train_ards_detector.py:416-422, 474-476) on the same 4 rotating batches of 8 sequences: the bf16 B200 trainer against
+    torch.optim.SGD on the fp32 CPU oracle.  The headline number is a bf16 TRAINING rate, so the claim to check is that the
+    trajectory -- not just one step -- follows fp32: per-step loss within a band, the smoothed curves within a tighter
+    one, and both runs must actually learn."""
+    from deepards_b200.data_parallel import DataParallelTrainer
+    steps, B = 200, 8
+    kw = dict(initial_planes=16) if backbone == "resnet18" else {}
+    sd0 = O.cnn_linear_state(backbone, seed=41, bn_perturb=0.1, **kw)
+    batches = [(O.synthetic_breaths(B, seed=600 + i), O.synthetic_targets(B, seed=600 + i)) for i in range(4)]
+    # learnable signal: the class decides the sign of a small offset on every breath of the sequence
+    batches = [(x + 0.5 * (t[:, :1] * 2 - 1).view(B, 1, 1, 1), t) for x, t in batches]
+    ref = {k: v.clone() for k, v in sd0.items()}
+    names = [k for k, v in ref.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    leaves = {k: ref[k].clone().requires_grad_(True) for k in names}
+    opt = torch.optim.SGD([leaves[k] for k in names], lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    ref_losses = []
+    for i in range(steps):
+        x, t = batches[i % 4]
+        cur = dict(ref)
+        cur.update({k: leaves[k].detach() for k in names})
+        _, loss, grads = O.forward_backward(cur, x, t, clip_val=0.01, running_update=backbone == "resnet18")
+        ref_losses.append(float(loss))
+        opt.zero_grad()
+        for k in names:
+            leaves[k].grad = grads[k].clone() if k in grads else None
+        opt.step()
+    import deepards_b200 as D
+    bb = D.resnet18(**kw) if backbone == "resnet18" else D.densenet18(drop_rate=0.0)
+    net = D.CNNLinearNetwork(bb, 20, 0)
+    net.load_state_dict({k: v.clone() for k, v in sd0.items()})
+    net = net.cuda().train()
+    net.precision = "bf16"
+    tr = DataParallelTrainer(net, lr=1e-3, optimizer="sgd", weight_decay=1e-4, clip_val=0.01, use_graph=True)
+    dev = [(x.cuda(), t.cuda()) for x, t in batches]
+    losses = [float(tr.train_step(*dev[i % 4])) for i in range(steps)]
+    a, b = torch.tensor(losses), torch.tensor(ref_losses)
+    smooth = lambda v: v.unfold(0, 20, 1).mean(1)  # noqa: E731
+    d_step = float((a - b).abs().max())
+    d_smooth = float((smooth(a) - smooth(b)).abs().max())
+    print("%s bf16 trajectory: loss %.4f -> %.4f (fp32 oracle %.4f -> %.4f); max |dloss| per step %.4f, smoothed %.4f" %
+          (backbone, float(a[:8].mean()), float(a[-8:].mean()), float(b[:8].mean()), float(b[-8:].mean()), d_step, d_smooth))
+    assert float(b[-8:].mean()) < float(b[:8].mean()) - 0.02, "the fp32 oracle run did not learn: the test has no signal"
+    assert float(a[-8:].mean()) < float(a[:8].mean()) - 0.02
+    # measured: ResNet-18 0.0054 / 0.0025, DenseNet-18 0.0122 / 0.0064 (profiles/r02_parity_report.txt)
+    assert d_step <= 0.025, d_step
+    assert d_smooth <= 0.013, d_smooth
+
+
+def test_reference_clamp_hooks_on_every_parameter_incl_the_unused_ones():
+    """train_ards_detector.py:474-476 registers `lambda grad: torch.clamp(grad, -clip, clip)` on EVERY parameter.  ResNet's
+    conv1_alt / conv2 / bn2 never take part in forward(): like in the reference they are not in the autograd graph, their
+    hook is never called (a None gradient would make clamp raise) and their .grad stays None; the optimizer skips them."""
+    import deepards_b200 as D
+    torch.manual_seed(0)
+    net = D.CNNLinearNetwork(D.resnet18(initial_planes=16), 20, 0).cuda().train()
+    net.precision = "fp32"
+    calls = []
+    for n, p in net.named_parameters():
+        p.register_hook(lambda g, n=n: (calls.append(n), torch.clamp(g, -0.01, 0.01))[1])
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    x, t = O.synthetic_breaths(3, seed=9).cuda(), O.synthetic_targets(3, seed=9).cuda()
+    for _ in range(2):
+        opt.zero_grad()
+        F.binary_cross_entropy_with_logits(net(x, None), t).backward()
+        opt.step()
+    unused = [n for n, p in net.named_parameters() if p.grad is None]
+    assert sorted(unused) == sorted(n for n, _ in net.named_parameters()
+                                    if n.startswith(("breath_block.conv1_alt.", "breath_block.conv2.", "breath_block.bn2.")))
+    assert not set(unused) & set(calls)
+    assert all(float(p.grad.abs().max()) <= 0.01 + 1e-9 for p in net.parameters() if p.grad is not None)
