@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdeepards_b200.so")
 
 F32, BF16 = 0, 1
 HINT_LAST_USE = 0x100   # DARDS_HINT_LAST_USE: OR-ed into `impl` (conv fwd / dgrad) or `relu` (gbn_fwd)
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 P, I, LL, ULL, F, D = c_void_p, c_int, c_longlong, c_ulonglong, c_float, c_double
 
@@ -53,7 +53,7 @@ _SIGNATURES = {
     "dards_avgpool2_bwd": [P, P, I, I, I, I, I, I, P],
     "dards_avgpool_full_fwd": [P, P, I, I, I, I, I, P],
     "dards_avgpool_full_bwd": [P, P, I, I, I, I, I, P],
-    "dards_dropout": [P, I, I, I, F, ULL, P, I, P],
+    "dards_dropout": [P, I, I, I, F, ULL, P, I, I, P],
     "dards_linear_fwd": [P, P, P, P, I, I, I, P],
     "dards_linear_bwd": [P, P, P, P, P, P, I, I, I, I, P],
     "dards_bce_with_logits": [P, P, P, P, I, F, P],

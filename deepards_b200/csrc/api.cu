@@ -67,7 +67,7 @@ int launch_stem_bwd(const void*, const float*, const float*, const float*, const
 int launch_avgpool2(int, const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int launch_avgpool_full_fwd(const void*, float*, int, int, int, int, int, cudaStream_t);
 int launch_avgpool_full_bwd(const float*, void*, int, int, int, int, int, cudaStream_t);
-int launch_dropout(void*, int, int, int, float, unsigned long long, const unsigned long long*, int, cudaStream_t);
+int launch_dropout(void*, int, int, int, float, unsigned long long, const unsigned long long*, int, int, cudaStream_t);
 int launch_bce(const float*, const float*, float*, float*, int, float, cudaStream_t);
 int launch_linear_fwd(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int launch_linear_bwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, int,
@@ -89,7 +89,7 @@ using namespace dards;
 
 extern "C" {
 
-int dards_version(void) { return 5; }
+int dards_version(void) { return 6; }
 
 const char* dards_last_error(void) { return g_err; }
 
@@ -327,9 +327,10 @@ int dards_avgpool_full_bwd(const float* dfeat, void* din, int n_breaths, int l, 
 }
 
 int dards_dropout(void* x, int n_rows, int c, int stride, float p, unsigned long long seed,
-                  const unsigned long long* seed_offset_dev, int dtype, void* stream) {
+                  const unsigned long long* seed_offset_dev, int rows_per_seq, int dtype, void* stream) {
   DARDS_CHECK_ARG(x, "dropout: null pointer");
-  return launch_dropout(x, n_rows, c, stride, p, seed, seed_offset_dev, dtype, S(stream));
+  DARDS_CHECK_ARG(rows_per_seq >= 0, "dropout: negative rows_per_seq");
+  return launch_dropout(x, n_rows, c, stride, p, seed, seed_offset_dev, rows_per_seq, dtype, S(stream));
 }
 
 int dards_bce_with_logits(const float* logits, const float* target, float* loss, float* dlogits, int n,

@@ -92,22 +92,36 @@ __global__ void avgpool_full_bwd_bf16x8_kernel(const float* __restrict__ dfeat, 
   }
 }
 
-// ---- dropout: keep-mask is a pure function of (seed, element index) ---------------------------------------
-__device__ __forceinline__ uint32_t mix32(uint64_t z) {
-  // splitmix64 finaliser
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+// ---- dropout: keep-mask is a pure function of (seed, step, GLOBAL element index) ------------------------------
+// Philox4x32-10 (Salmon et al., the generator behind torch's CUDA dropout): key = seed ^ step-dependent offset, counter =
+// global element index / 4; element e takes word e % 4 of its block.  "Global" = counted from the first sequence of the
+// whole (all-ranks) batch: a rank adds first_sequence * rows_per_seq to its local row index, so the masks do not depend
+// on how the batch is sharded and the backward regenerates them from the same three numbers.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
 // VEC consecutive channels per thread (a 16-byte access when the slice allows it, else scalar); the random number of
-// an element depends only on (seed, row * c + channel), never on the vector width.
+// an element depends only on (seed, step, global row * c + channel), never on the vector width.
 template <typename T, int VEC>
 __global__ void dropout_kernel(T* __restrict__ x, long long n_rows, int c, int stride, float p, float scale,
-                               unsigned long long seed, const unsigned long long* __restrict__ seed_off) {
-  if (seed_off) seed += *seed_off * 0x9E3779B97F4A7C15ull;
+                               unsigned long long seed, const unsigned long long* __restrict__ seed_off, int rows_per_seq) {
+  unsigned long long row0 = 0;
+  if (seed_off) {
+    seed += seed_off[0] * 0x9E3779B97F4A7C15ull;
+    if (rows_per_seq > 0) row0 = seed_off[1] * (unsigned long long)rows_per_seq;
+  }
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const int cv = c / VEC;
   const long long total = n_rows * cv;
   const uint32_t thresh = (uint32_t)(p * 4294967296.0);
@@ -118,11 +132,18 @@ __global__ void dropout_kernel(T* __restrict__ x, long long n_rows, int c, int s
     T v[VEC];
     if (VEC > 1) *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(ptr);
     else v[0] = *ptr;
+    const unsigned long long e0 = (row0 + (unsigned long long)r) * (unsigned long long)c + (unsigned long long)cc;
+    uint32_t rnd[4];
+    unsigned long long blk = ~0ull;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const uint32_t rnd = mix32(seed ^ ((uint64_t)(r * c + cc + j) * 0xD1342543DE82EF95ull));
+      const unsigned long long e = e0 + j;
+      if ((e >> 2) != blk) {   // VEC and cc are multiples of 4 on the vector path: one Philox block per 4 elements
+        blk = e >> 2;
+        philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), 0u, 0u, k0, k1, rnd);
+      }
       const float f = Elem<T>::ld(&v[j]);
-      Elem<T>::st(&v[j], rnd < thresh ? 0.f : f * scale);
+      Elem<T>::st(&v[j], rnd[e & 3] < thresh ? 0.f : f * scale);
     }
     if (VEC > 1) *reinterpret_cast<uint4*>(ptr) = *reinterpret_cast<const uint4*>(v);
     else *ptr = v[0];
@@ -336,7 +357,7 @@ int launch_avgpool_full_bwd(const float* dfeat, void* din, int n_breaths, int l,
 }
 
 int launch_dropout(void* x, int n_rows, int c, int stride, float p, unsigned long long seed,
-                   const unsigned long long* seed_off, int dtype, cudaStream_t st) {
+                   const unsigned long long* seed_off, int rows_per_seq, int dtype, cudaStream_t st) {
   DARDS_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0,1)");
   if (n_rows == 0 || p == 0.f) return DARDS_OK;
   DARDS_DISPATCH_DTYPE(dtype, {
@@ -344,10 +365,10 @@ int launch_dropout(void* x, int n_rows, int c, int stride, float p, unsigned lon
     const bool vec_ok = c % VEC == 0 && stride % VEC == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     if (vec_ok)
       dropout_kernel<T, VEC><<<grid_for((long long)n_rows * (c / VEC), 256), 256, 0, st>>>(
-          static_cast<T*>(x), n_rows, c, stride, p, 1.f / (1.f - p), seed, seed_off);
+          static_cast<T*>(x), n_rows, c, stride, p, 1.f / (1.f - p), seed, seed_off, rows_per_seq);
     else
       dropout_kernel<T, 1><<<grid_for((long long)n_rows * c, 256), 256, 0, st>>>(static_cast<T*>(x), n_rows, c, stride, p,
-                                                                                 1.f / (1.f - p), seed, seed_off);
+                                                                                 1.f / (1.f - p), seed, seed_off, rows_per_seq);
   })
   DARDS_CHECK_LAUNCH("dropout");
   return DARDS_OK;

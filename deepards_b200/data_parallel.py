@@ -205,6 +205,10 @@ class DataParallelTrainer(object):
         if plan.__dict__.setdefault("_dp_grad_scale", gs) != gs:
             raise RuntimeError("deepards_b200: this plan (%d sequences per rank) was first used with a different global "
                                "batch size; the loss scale is part of its captured CUDA graphs" % x.shape[0])
+        if plan.dropout and self.world > 1:
+            # dropout masks are keyed by the global sequence index: same masks whatever the number of ranks
+            first = shard_bounds(int(global_batch), self.world, self.rank)[0] if global_batch is not None else self.rank * x.shape[0]
+            plan.set_sequence_offset(first)
         if scaling is None:
             plan.load_input(x)
         else:
@@ -328,7 +332,7 @@ class DataParallelTrainer(object):
             st = plan._stream()
             plan.pack.run(st)
             if plan.dropout:
-                plan.seed_dev.add_(1)
+                plan.seed_dev[0:1].add_(1)
             plan.fwd.run(st)
             _lib.call("dards_bce_with_logits", plan.logits.data_ptr(), t_static.data_ptr(), self.loss_buf.data_ptr(),
                       plan.dlogits.data_ptr(), plan.logits.numel(), plan.__dict__.get("_dp_grad_scale", 1.0), st)

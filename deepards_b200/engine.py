@@ -38,7 +38,11 @@ def _multi_rank():
 
 
 def default_precision():
-    return os.environ.get("DEEPARDS_B200_PRECISION", "fp32")
+    """Storage / arithmetic of a network whose `.precision` was not set.  "bf16" (the default): bf16 activations,
+    tcgen05 convolutions, fp32 statistics / gradients / weights -- the path bench.py measures; logits within 5e-2 and a
+    200-step loss trajectory within 1.3e-2 of the fp32 reference (tests/test_model_parity_gpu.py).  "fp32"
+    (DEEPARDS_B200_PRECISION=fp32 or `net.precision = "fp32"`): the 1e-4 parity path on the CUDA cores, ~14x slower."""
+    return os.environ.get("DEEPARDS_B200_PRECISION", "bf16")
 
 
 def _conv_impl_override():
@@ -118,7 +122,9 @@ class Plan(object):
 
         # ---- I/O buffers ------------------------------------------------------------------------------------
         self.x_buf = self.new((n_breaths, SEQ_LEN), torch.float32)
-        self.seed_dev = self.new((1,), torch.int64, zero=True)
+        # [0] forward counter (fresh dropout masks per step), [1] global index of this rank's first sequence
+        self.seed_dev = self.new((2,), torch.int64, zero=True)
+        self._seq_offset = 0
         self._running = []   # (mean, rstd, bn, rows, c): running-statistics updates, one batched launch per forward
         self._pending_red = []  # (partial table, rows, c, destination pointer): flushed as one batched launch
         kind = backbone.network_name
@@ -583,7 +589,7 @@ class Plan(object):
                     drop_id += 1
                     seed = 0x5DEECE66D * drop_id + 11
                     self.fwd.add("dards_dropout", cat.data_ptr() + cin * esz, N * L, g, ctot, drop_p, seed,
-                                 self.seed_dev.data_ptr(), self.dt)
+                                 self.seed_dev.data_ptr(), self.group * L, self.dt)
                 self.sites["%s.%s.relu1" % (bname, lname)] = a
                 self.sites["%s.%s.relu2" % (bname, lname)] = b
                 lrecs.append(dict(layer=layer, c1=c1, c2=c2, a=a, st1=st1, y1=y1, b=b, st2=st2, cin=cin, mid=mid, g=g,
@@ -643,7 +649,7 @@ class Plan(object):
                 dnew = d_cat.data_ptr() + cin * esz  # (N, L, g) slice, row stride ctot
                 if lr["seed"] is not None:
                     self.bwd.add("dards_dropout", dnew, N * L, g, ctot, lr["drop_p"], lr["seed"], self.seed_dev.data_ptr(),
-                                 self.dt)
+                                 self.group * L, self.dt)
                 self.conv_wgrad(lr["c2"], lr["b"].data_ptr(), mid, dnew, ctot, L)
                 db = self.scratch("d_mid", (N, L, mid))
                 self.conv_dgrad(lr["c2"], dnew, ctot, db.data_ptr(), mid, L)
@@ -718,19 +724,62 @@ class Plan(object):
         _lib.call("dards_scale_windows", raw.data_ptr(), 1 if raw.dtype == torch.float64 else 0, self.x_buf.data_ptr(),
                   raw.numel(), float(mu), float(std), 1 if padded else 0, self._stream())
 
+    # The autograd path (`net(x)` -> loss.backward(), what train_ards_detector.py drives) replays the recorded forward and
+    # backward as two CUDA graphs after two eager calls: ~260 launches issued one by one from Python through ctypes
+    # otherwise.  The weight re-packing launch is part of the forward graph, i.e. it runs on EVERY forward: the packed
+    # copies can then never be stale, whatever edits the parameters between two calls (optimizer.step(), `.data` edits,
+    # weight averaging, ...).  DEEPARDS_B200_PLAN_GRAPH=0 keeps everything eager.
+    def _graph_for(self, which, run):
+        if os.environ.get("DEEPARDS_B200_PLAN_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return None     # inside somebody else's capture (the trainer's whole-step graph): just record the launches
+        st = self.__dict__.setdefault("_graphs", {})
+        ent = st.setdefault(which, {"calls": 0, "graph": None})
+        if ent["graph"] is None:
+            ent["calls"] += 1
+            if ent["calls"] <= 2:
+                return None
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run(self._stream())
+            ent["graph"] = g
+        return ent["graph"]
+
+    def drop_graphs(self):
+        self.__dict__.pop("_graphs", None)
+
+    def set_sequence_offset(self, first_sequence):
+        """Index of this call's first sequence in the global (all-ranks) batch: the dropout masks are keyed by the global
+        sequence index, so a sharded step draws the masks of the unsharded one."""
+        first_sequence = int(first_sequence)
+        if first_sequence != self._seq_offset:
+            self.seed_dev[1] = first_sequence
+            self._seq_offset = first_sequence
+
     def run_forward(self):
-        st = self._stream()
-        self._pack_if_needed(st)
         if self.dropout:
-            self.seed_dev.add_(1)
-        self.fwd.run(st)
+            self.seed_dev[0:1].add_(1)
+
+        def run(st):
+            self.pack.run(st)
+            self.fwd.run(st)
+
+        g = self._graph_for("fwd", run)
+        if g is not None:
+            g.replay()
+        else:
+            run(self._stream())
         self.fwd_serial += 1
 
     def run_backward(self):
         if self.bwd_serial == self.fwd_serial:
             raise RuntimeError("backward() without a new forward(): forward #%d has already been back-propagated "
                                "(in-place backward kernels consumed its buffers)" % self.fwd_serial)
-        self.bwd.run(self._stream())
+        g = self._graph_for("bwd", self.bwd.run)
+        if g is not None:
+            g.replay()
+        else:
+            self.bwd.run(self._stream())
         self.bwd_serial = self.fwd_serial
 
     def mark_no_backward(self):

@@ -222,10 +222,10 @@ def avgpool_full_bwd(dfeat, l, dtype):
     return din
 
 
-def dropout_(x, p, seed, seed_dev=None):
+def dropout_(x, p, seed, seed_dev=None, rows_per_seq=0):
     n, l, c = x.shape
     _lib.call("dards_dropout", x.data_ptr(), n * l, c, _rowstride(x), p, seed,
-              seed_dev.data_ptr() if seed_dev is not None else None, _dt(x), _st(x))
+              seed_dev.data_ptr() if seed_dev is not None else None, rows_per_seq, _dt(x), _st(x))
     return x
 
 

@@ -82,7 +82,7 @@ class ResNet(_Picklable, nn.Module):
                 m.bias.data.zero_()
         self.n_out_filters = self.inplanes * block.expansion
         self.network_name = 'resnet'
-        self.precision = None  # None -> DEEPARDS_B200_PRECISION or 'fp32'; 'bf16' selects the tcgen05 path
+        self.precision = None  # None -> DEEPARDS_B200_PRECISION or 'bf16' (tcgen05 path); 'fp32' = the 1e-4 parity path
 
     def _stage(self, block, planes, n_blocks, stride):
         ds = None

@@ -211,12 +211,13 @@ int dards_avgpool_full_fwd(const void* in, float* feat, int n_breaths, int l, in
                            void* stream);
 int dards_avgpool_full_bwd(const float* dfeat, void* din, int n_breaths, int l, int c, int din_stride, int dtype,
                            void* stream);
-/* F.dropout(p, training=True) (densenet.py:37-39) in place on a channel slice; the mask is a pure
- * function of (seed, element index) so the backward regenerates it. */
+/* F.dropout(p, training=True) (densenet.py:37-39) in place on a channel slice; the keep-mask is Philox4x32-10 keyed by
+ * (seed, step, GLOBAL element index), so the backward regenerates it and it does not depend on how a batch is sharded over
+ * ranks.  seed_offset_dev (nullable) points to TWO 64-bit words on the device: [0] a step counter mixed
+ * into the key (a captured CUDA graph draws a fresh mask on every replay), [1] the index of this rank's first sequence in
+ * the global batch; rows_per_seq = rows of x per sequence (group * L; 0 = ignore [1]). */
 int dards_dropout(void* x, int n_rows, int c, int stride, float p, unsigned long long seed,
-                  const unsigned long long* seed_offset_dev /* nullable: added to seed on the device, so a
-                  captured CUDA graph draws a fresh mask on every replay */,
-                  int dtype, void* stream);
+                  const unsigned long long* seed_offset_dev, int rows_per_seq, int dtype, void* stream);
 
 /* ---- linear head --------------------------------------------------------------------- */
 /* nn.Linear(K,2) on flattened features (torch_cnn_linear_network.py:102,110 and :55,63):

@@ -19,10 +19,12 @@ def _worker(rank, world, port, backbone, use_graph, q):
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     solo = dist.new_group([0])          # collective call on every rank; only rank 0 is a member
+    dropout = backbone.endswith("+dropout")     # densenet.py:33-39 active: the masks are keyed by the global sequence index
+    backbone = backbone.split("+")[0]
     sd = O.cnn_linear_state(backbone, seed=41, bn_perturb=0.1, **({"initial_planes": 16} if backbone == "resnet18" else {}))
 
     def make():
-        bb = D.resnet18(initial_planes=16) if backbone == "resnet18" else D.densenet18(drop_rate=0.0)
+        bb = D.resnet18(initial_planes=16) if backbone == "resnet18" else D.densenet18(drop_rate=0.2 if dropout else 0.0)
         net = D.CNNLinearNetwork(bb, 20, 0)
         net.load_state_dict(sd)
         net = net.cuda().train()
@@ -48,7 +50,8 @@ def _worker(rank, world, port, backbone, use_graph, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("backbone,use_graph", [("resnet18", False), ("resnet18", True), ("densenet18", True)])
+@pytest.mark.parametrize("backbone,use_graph", [("resnet18", False), ("resnet18", True), ("densenet18", True),
+                                                ("densenet18+dropout", True)])
 def test_two_rank_step_equals_single_process_step(backbone, use_graph):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

@@ -497,9 +497,21 @@ def test_dropout_mask_is_reproducible_and_unbiased():
     kept = (a > 0).float().mean().item()
     assert abs(kept - 0.8) < 0.01
     assert abs(float(a.max()) - 1.25) < 1e-6
-    off = torch.tensor([5], dtype=torch.int64, device=DEV)
+    off = torch.tensor([5, 0], dtype=torch.int64, device=DEV)     # [step counter, first sequence]
     d = K().dropout_(x.clone(), 0.2, 1234, off)
     assert not torch.equal(a, d)
+    # keyed by the GLOBAL element index: the second half of the batch, run as its own shard with
+    # first_sequence = 2 (of 4 sequences x 16 breaths x 28 rows), draws exactly the masks it has inside the whole batch;
+    # a channel slice of a wider buffer and bf16 storage do not change them either
+    rows_per_seq = 16 * 28
+    whole = K().dropout_(x.clone(), 0.2, 1234, torch.tensor([7, 0], dtype=torch.int64, device=DEV), rows_per_seq)
+    shard = K().dropout_(x[32:].clone(), 0.2, 1234, torch.tensor([7, 2], dtype=torch.int64, device=DEV), rows_per_seq)
+    assert torch.equal(whole[32:], shard)
+    wide = torch.ones(64, 28, 96, device=DEV)
+    K().dropout_(wide[:, :, 64:96], 0.2, 1234, torch.tensor([7, 0], dtype=torch.int64, device=DEV), rows_per_seq)
+    assert torch.equal(wide[:, :, 64:96], whole) and float(wide[:, :, :64].min()) == 1.0
+    hb = K().dropout_(x.clone().bfloat16(), 0.2, 1234, torch.tensor([7, 0], dtype=torch.int64, device=DEV), rows_per_seq)
+    assert torch.equal(hb > 0, whole > 0)
 
 
 def test_fused_optimizers_match_torch():

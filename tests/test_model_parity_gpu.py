@@ -383,3 +383,36 @@ def test_reference_clamp_hooks_on_every_parameter_incl_the_unused_ones():
                                     if n.startswith(("breath_block.conv1_alt.", "breath_block.conv2.", "breath_block.bn2.")))
     assert not set(unused) & set(calls)
     assert all(float(p.grad.abs().max()) <= 0.01 + 1e-9 for p in net.parameters() if p.grad is not None)
+
+
+def test_dropout_masks_do_not_depend_on_the_sharding():
+    """DenseNet in train() mode (drop_rate 0.2 active, densenet.py:33-39): the masks are keyed by the global sequence
+    index, so running sequences [2, 4) of a batch as their own call with sequence offset 2 reproduces their logits inside
+    the whole batch bit for bit -- the single-GPU statement of "a 2-rank step equals the 1-rank step with dropout on"
+    (tests/test_dp_multi_gpu.py checks the real thing on two devices)."""
+    import deepards_b200 as D
+    from deepards_b200 import engine
+    sd = O.cnn_linear_state("densenet18", seed=51, bn_perturb=0.1)
+    x = O.synthetic_breaths(4, seed=77).cuda()
+
+    def run(xs, first):
+        torch.manual_seed(0)
+        net = D.CNNLinearNetwork(D.densenet18(), 20, 0)
+        net.load_state_dict(sd)
+        net = net.cuda().train()
+        net.precision = "bf16"
+        from deepards_b200.torch_cnn_linear_network import _drop_key
+        plan = engine.get_plan(net, net.breath_block, net.linear_final, xs.shape[0] * 20, 20, "bf16", "cnn_linear",
+                               dropout=_drop_key(net.breath_block), update_running=True)
+        assert plan.dropout
+        plan.set_sequence_offset(first)
+        plan.load_input(xs)
+        plan.run_forward()
+        plan.mark_no_backward()
+        torch.cuda.synchronize()
+        return plan.logits.clone()
+
+    whole = run(x, 0)
+    assert torch.equal(run(x[2:], 2), whole[2:])
+    assert torch.equal(run(x[:2], 0), whole[:2])
+    assert not torch.equal(run(x[2:], 0), whole[2:])      # without the offset the shard would reuse the masks of [0, 2)
