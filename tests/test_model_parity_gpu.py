@@ -253,6 +253,7 @@ def test_dropout_training_mode_is_stochastic_but_eval_like_when_off():
     net = D.CNNLinearNetwork(D.densenet18(), 20, 0)
     net.load_state_dict(sd)
     net = net.cuda().train()
+    net.precision = "fp32"
     x = O.synthetic_breaths(2, seed=2).cuda()
     with torch.no_grad():
         a, b = net(x, None), net(x, None)
