@@ -10,11 +10,13 @@ plus the data-parallel trainer (data_parallel.DataParallelTrainer) that replaces
 from .resnet import resnet18, resnet34, ResNet, BasicBlock  # noqa: F401
 from .densenet import densenet18, densenet121, DenseNet  # noqa: F401
 from .torch_cnn_linear_network import (CNNLinearNetwork, CNNSingleBreathLinearNetwork, CNNLinearToMean,  # noqa: F401
-                                       CNNLinearComprToRF, CNNDoubleLinearNetwork, CNNRegressor, CNNLSTMNetwork)
+                                       CNNLinearComprToRF, CNNDoubleLinearNetwork, CNNRegressor, CNNLSTMNetwork,
+                                       CNNTransformerNetwork)
 from .input_pipeline import WindowScaler  # noqa: F401
 from . import gradcam  # noqa: F401
+from .patient_votes import patient_vote_table  # noqa: F401
 from .registry import base_networks, network_heads, install  # noqa: F401
 
 __all__ = ["resnet18", "resnet34", "densenet18", "densenet121", "ResNet", "DenseNet", "BasicBlock", "CNNLinearNetwork",
            "CNNSingleBreathLinearNetwork", "CNNLinearToMean", "CNNLinearComprToRF", "CNNDoubleLinearNetwork",
-           "CNNRegressor", "CNNLSTMNetwork", "WindowScaler", "gradcam", "base_networks", "network_heads", "install"]
+           "CNNRegressor", "CNNLSTMNetwork", "CNNTransformerNetwork", "patient_vote_table", "WindowScaler", "gradcam", "base_networks", "network_heads", "install"]

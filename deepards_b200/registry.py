@@ -9,7 +9,7 @@ package with no other change (INTEGRATION.md shows the two-line edit a maintaine
 from .densenet import densenet18, densenet121
 from .resnet import resnet18, resnet34
 from .torch_cnn_linear_network import (CNNDoubleLinearNetwork, CNNLinearComprToRF, CNNLinearNetwork, CNNLinearToMean,
-                                       CNNLSTMNetwork, CNNRegressor, CNNSingleBreathLinearNetwork)
+                                       CNNLSTMNetwork, CNNRegressor, CNNSingleBreathLinearNetwork, CNNTransformerNetwork)
 
 base_networks = {
     'resnet18': resnet18,
@@ -27,6 +27,7 @@ network_heads = {
     'cnn_double_linear': CNNDoubleLinearNetwork,
     'cnn_regressor': CNNRegressor,
     'cnn_lstm': CNNLSTMNetwork,
+    'cnn_transformer': CNNTransformerNetwork,
 }
 
 
@@ -35,6 +36,7 @@ def install(train_module):
     train_module.base_networks.update(base_networks)
     train_module.CNNLinearNetwork = CNNLinearNetwork
     train_module.CNNSingleBreathLinearNetwork = CNNSingleBreathLinearNetwork
-    for cls in (CNNLinearToMean, CNNLinearComprToRF, CNNDoubleLinearNetwork, CNNRegressor, CNNLSTMNetwork):
+    for cls in (CNNLinearToMean, CNNLinearComprToRF, CNNDoubleLinearNetwork, CNNRegressor, CNNLSTMNetwork,
+                CNNTransformerNetwork):
         setattr(train_module, cls.__name__, cls)
     return train_module

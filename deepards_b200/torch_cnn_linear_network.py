@@ -162,3 +162,95 @@ class CNNLSTMNetwork(_HeadBase):
         with torch.backends.cudnn.flags(allow_tf32=_ag.module_precision(self) == "bf16"):
             out, (hx, cx) = self.lstm(feat, hx_cx)
         return self.linear_final(out), (hx, cx)
+
+
+# ---- transformer head (deepards/models/cnn_transformer.py:8-44 over deepards/models/transformer.py) -------------------
+class _SelfAttention(nn.Module):
+    """Multi-head scaled dot-product attention with the reference's parameter names (transformer.py:13-58)."""
+
+    def __init__(self, input_size, hidden_size, num_heads):
+        super(_SelfAttention, self).__init__()
+        if hidden_size % num_heads:
+            raise ValueError("hidden_size must be a multiple of num_heads")
+        self.num_heads, self.head_size = num_heads, hidden_size // num_heads
+        self.q_linear = nn.Linear(input_size, hidden_size)
+        self.k_linear = nn.Linear(input_size, hidden_size)
+        self.v_linear = nn.Linear(input_size, hidden_size)
+        self.joint_linear = nn.Linear(hidden_size, input_size)
+        self.weights = None
+
+    def forward(self, x):
+        b, s, _ = x.shape
+        split = lambda t: t.view(b, s, self.num_heads, self.head_size).permute(0, 2, 1, 3)  # noqa: E731
+        q, k, v = split(self.q_linear(x)), split(self.k_linear(x)), split(self.v_linear(x))
+        att = torch.softmax(torch.einsum("bhid,bhjd->bhij", q, k) / float(self.head_size) ** 0.5, dim=-1)
+        self.weights = att  # the reference keeps the last attention map for visualisation
+        mixed = torch.einsum("bhij,bhjd->bihd", att, v).reshape(b, s, self.num_heads * self.head_size)
+        return self.joint_linear(mixed)
+
+
+class _TransformerBlock(nn.Module):
+    """attention -> dropout -> +x -> LayerNorm; feed-forward(ReLU) -> dropout -> +x (the block INPUT, as the reference
+    does, transformer.py:89-91) -> LayerNorm."""
+
+    def __init__(self, input_size, hidden_size, num_heads, dropout):
+        super(_TransformerBlock, self).__init__()
+        self.attention = _SelfAttention(input_size, hidden_size, num_heads)
+        self.attention_norm = nn.LayerNorm(input_size)
+        self.attention_dropout = nn.Dropout(dropout)
+        self.ff = nn.Sequential(nn.Linear(input_size, hidden_size), nn.ReLU(), nn.Linear(hidden_size, input_size),
+                                nn.Dropout(dropout))
+        self.ff_norm = nn.LayerNorm(input_size)
+
+    def forward(self, x):
+        attended = self.attention_norm(self.attention_dropout(self.attention(x)) + x)
+        return self.ff_norm(self.ff(attended) + x)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, input_size, hidden_size, num_blocks, num_heads, dropout=.2):
+        super(_Transformer, self).__init__()
+        self.blocks = nn.Sequential(*[_TransformerBlock(input_size, hidden_size, num_heads, dropout)
+                                      for _ in range(num_blocks)])
+
+    def forward(self, x):
+        return self.blocks(x)
+
+
+class CNNTransformerNetwork(_HeadBase):
+    """Transformer over the sequence's breath features, Linear(F, 2) on every position -> (B, S, 2)
+    (cnn_transformer.py:8-44).  The backbone is ONE batched plan with BatchNorm group S; the transformer (a few hundred
+    kB of weights, S = 20 tokens) stays in torch.  Breath metadata is not supported on this backend (the reference skips
+    it when it is NaN, which is what the experiment files feed, cnn_transformer.py:31)."""
+
+    def __init__(self, breath_block, metadata_features, bm_to_linear, hidden_units, num_blocks):
+        super(CNNTransformerNetwork, self).__init__()
+        if metadata_features:
+            raise NotImplementedError("deepards_b200: metadata_features > 0 is not implemented")
+        self.seq_size = 224
+        self.breath_block = breath_block
+        self.bm_to_linear = bm_to_linear
+        self.transformer = _Transformer(breath_block.n_out_filters, hidden_units, num_blocks, 4)
+        self.linear_final = nn.Linear(breath_block.n_out_filters, 2)
+
+    def forward(self, x, metadata=None):
+        if metadata is not None and not torch.any(torch.isnan(metadata)):
+            raise NotImplementedError("deepards_b200: breath metadata is not implemented on this backend")
+        feat = self._sequence_features(x)
+        with _no_tf32(self):
+            return self.linear_final(self.transformer(feat))
+
+
+class _no_tf32(object):
+    """fp32 plans promise the reference's fp32 numbers: keep cuBLAS out of TF32 for the head's small GEMMs."""
+
+    def __init__(self, mod):
+        self.on = _ag.module_precision(mod) != "bf16"
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        if self.on:
+            torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *a):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev

@@ -528,3 +528,31 @@ def synthetic_targets(n_seq: int, seed: int = 1234) -> torch.Tensor:
     gen = torch.Generator().manual_seed(seed + 1)
     cls = (torch.rand(n_seq, generator=gen) < 0.5).long()
     return F.one_hot(cls, 2).float()
+
+
+def patient_vote_table(patient, y_true, y_pred, n_classes=2):
+    """CPU restatement of the per-patient loop of DeepARDSResults.perform_patient_predictions (deepards/metrics.py:572-600,
+    helpers get_tps/get_fps/get_tns/get_fns :29-62): patients in order of first appearance (`y_test.patient.unique()`); per
+    class n the counts over the patient's windows of (actual == n & pred == n), (actual != n & pred == n),
+    (actual != n & pred != n), (actual == n & pred != n) and the votes (pred == n); prediction = np.argmax(votes),
+    pred_frac = votes[1] / sum(votes).  Returns an (n_patients, 2 + 5 * n_classes + 2) float64 table with the reference's
+    column order: patient, patho, [tps, fps, tns, fns, votes] per class, prediction, pred_frac."""
+    import numpy as np
+    patient, y_true, y_pred = (np.asarray(a) for a in (patient, y_true, y_pred))
+    seen, rows = set(), []
+    for pt in patient:
+        if pt in seen:
+            continue
+        seen.add(pt)
+        m = patient == pt
+        actual, pred = y_true[m], y_pred[m]
+        row = [float(pt), float(actual[0])]                      # pt_rows.y.unique()[0]
+        votes = []
+        for n in range(n_classes):
+            row += [float(np.sum((actual == n) & (pred == n))), float(np.sum((actual != n) & (pred == n))),
+                    float(np.sum((actual != n) & (pred != n))), float(np.sum((actual == n) & (pred != n))),
+                    float(np.sum(pred == n))]
+            votes.append(row[-1])
+        row += [float(np.argmax(votes)), votes[1] / sum(votes)]
+        rows.append(row)
+    return np.array(rows, dtype=np.float64)

@@ -224,3 +224,56 @@ def test_sibling_heads_match_reference(kind):
     # small cases were chosen without such ties
     assert worst <= 5 * FP32_TOL, worst
     print("%s: worst gradient rel err %.2e" % (kind, worst))
+
+
+# ---- the last sibling components of SURVEY.md 8f-4 -----------------------------------------------------------------
+def test_transformer_head_matches_reference():
+    """CNNTransformerNetwork against the reference's own modules (deepards/models/cnn_transformer.py + transformer.py, run
+    under the Python-2 shim of oracle/make_golden_heads2.py): state_dict names, logits, loss, gradients."""
+    import deepards_b200 as D
+    z = _z("transformer_head")
+    sd = O.cnn_linear_state("resnet18", seed=9, bn_perturb=0.1, initial_planes=16, per_breath=True)
+    sd = {k: v for k, v in sd.items() if k.startswith("breath_block.")}
+    for k in z.files:
+        if k.startswith("sd/"):
+            sd[k[3:]] = torch.from_numpy(z[k])
+    net = D.CNNTransformerNetwork(D.resnet18(initial_planes=16), 0, False, 64, 2)
+    assert list(net.state_dict().keys()) == list(z["keys"])          # the reference's state_dict names and order
+    net.load_state_dict(sd, strict=True)
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    net = net.cuda().train()
+    net.precision = "fp32"
+    x = torch.from_numpy(z["x"]).cuda()
+    out = net(x, torch.tensor(float("nan")))
+    assert tuple(out.shape) == (2, 20, 2)
+    loss = F.binary_cross_entropy_with_logits(out, torch.from_numpy(z["target"]).cuda().unsqueeze(1).repeat(1, 20, 1))
+    loss.backward()
+    assert rel_err(out.detach().cpu(), z["logits"]) <= FP32_TOL
+    assert abs(float(loss) - float(z["loss"])) <= FP32_TOL
+    grads = {n: p.grad for n, p in net.named_parameters()}
+    worst = max(rel_err(grads[k[5:]].cpu(), z[k]) for k in z.files if k.startswith("grad/"))
+    print("transformer head: worst gradient rel err %.2e" % worst)
+    assert worst <= 5 * FP32_TOL      # through two LayerNorm + softmax blocks; the backbone gradients are held to 1e-4 elsewhere
+
+
+def test_patient_votes_on_device_match_the_references_loop():
+    import numpy as np
+    import deepards_b200 as D
+    z = _z("patient_votes")
+    t = D.patient_vote_table(torch.from_numpy(z["patient"]).cuda(), torch.from_numpy(z["y"]).cuda(),
+                             torch.from_numpy(z["pred"]).cuda())
+    cols = [str(c) for c in z["columns"]]
+    got = np.stack([t[c].double().cpu().numpy() for c in cols], axis=1)
+    assert np.array_equal(got, z["table"])
+    assert all(v.is_cuda for v in t.values())
+    # a big synthetic run against the CPU restatement: 300 patients, 200 k windows
+    g = torch.Generator().manual_seed(3)
+    pt = torch.randint(0, 300, (200_000,), generator=g) * 7 + 11
+    y = (pt % 3 == 0).long()
+    pr = (torch.rand(200_000, generator=g) < 0.4).long()
+    t = D.patient_vote_table(pt.cuda(), y.cuda(), pr.cuda())
+    ref = O.patient_vote_table(pt.numpy(), y.numpy(), pr.numpy())
+    got = np.stack([t[c].double().cpu().numpy() for c in cols], axis=1)
+    assert np.array_equal(got, ref)

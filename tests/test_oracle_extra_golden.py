@@ -78,3 +78,16 @@ def test_oracle_sibling_heads_equal_reference(kind):
     else:
         out = O.cnn_linear_forward(sd, x, head=kind)
     assert rel_err(out, z[kind + "/logits"]) < 1e-6
+
+
+def test_patient_vote_oracle_matches_the_references_own_loop():
+    """tests/golden/patient_votes.npz was produced by DeepARDSResults.perform_patient_predictions itself
+    (oracle/make_golden_heads2.py): arbitrary patient ids in interleaved order, a unanimous patient, a zero-vote patient and
+    an exact tie (np.argmax -> class 0)."""
+    import numpy as np
+    z = _z("patient_votes")
+    got = O.patient_vote_table(z["patient"], z["y"], z["pred"])
+    assert got.shape == z["table"].shape == (9, 14)
+    assert np.array_equal(got, z["table"])
+    tie = got[got[:, 6] == got[:, 11]]            # OTHER_votes == ARDS_votes
+    assert len(tie) >= 1 and (tie[:, 12] == 0.0).all() and (tie[:, 13] == 0.5).all()
