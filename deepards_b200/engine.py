@@ -22,6 +22,7 @@ import torch
 from . import _lib
 
 BN_EPS = 1e-5
+STEM_MAX_GROUP = 226   # stem.cu: forward 236, backward 226 breaths of 224 samples in shared memory
 BN_MOMENTUM = 0.1
 SEQ_LEN = 224
 
@@ -388,6 +389,14 @@ class Plan(object):
         c0 = conv.out_channels
         if conv.in_channels != 1 or conv.kernel_size[0] != 7 or conv.stride[0] != 2 or conv.padding[0] != 3:
             raise NotImplementedError("stem must be Conv1d(1, C0, 7, stride 2, padding 3)")
+        if self.group > STEM_MAX_GROUP:
+            # The fused stem keeps a BatchNorm group's input in shared memory (stem.cu).  Heads that call the backbone per
+            # sequence (group = 20) are far below the limit; a FLAT batch (ResNet.forward(x) / DenseNet.forward(x) /
+            # CNNRegressor: the whole batch is one BatchNorm group) is limited to this many breaths per call.
+            raise NotImplementedError(
+                "deepards_b200: a BatchNorm group of %d breaths exceeds the fused stem's limit of %d (its group input "
+                "lives in shared memory).  Call the backbone on at most %d breaths at a time, or through a sequence head "
+                "(group = sequence length)." % (self.group, STEM_MAX_GROUP, STEM_MAX_GROUP))
         mean, rstd = self.stats(c0)
         self.fwd.add("dards_stem_fwd", self.x_buf.data_ptr(), conv.weight.data_ptr(), bn.weight.data_ptr(),
                      bn.bias.data_ptr(), out, mean.data_ptr(), rstd.data_ptr(), self.G, self.group, c0, out_stride,

@@ -277,3 +277,15 @@ def test_patient_votes_on_device_match_the_references_loop():
     ref = O.patient_vote_table(pt.numpy(), y.numpy(), pr.numpy())
     got = np.stack([t[c].double().cpu().numpy() for c in cols], axis=1)
     assert np.array_equal(got, ref)
+
+
+def test_flat_batch_group_limit_is_a_clear_error():
+    """ResNet.forward(x) on a flat batch makes the whole batch one BatchNorm group; beyond 226 breaths the fused
+    stem cannot hold the group in shared memory -- that must be a clear error at plan build, not a kernel failure."""
+    import deepards_b200 as D
+    bb = D.resnet18(initial_planes=16).cuda().train()
+    bb.precision = "fp32"
+    with torch.no_grad():
+        assert tuple(bb(torch.randn(226, 1, 224, device="cuda")).shape) == (226, 128)
+        with pytest.raises(NotImplementedError, match="exceeds the fused stem's limit of 226"):
+            bb(torch.randn(240, 1, 224, device="cuda"))
