@@ -527,6 +527,10 @@ def kernel_roofline(trainer, x, t, args, backbone, steps=3):
                     n, l_in, l_out, cin, cout, k = a[6], a[7], a[8], a[9], a[10], a[13]
                     d["flops"] += 2.0 * n * l_out * cin * cout * k
                     d["bytes"] += esz * n * (l_in * cin + l_out * cout)
+                elif name == "dards_conv1d_wgrad_accum":
+                    n, l_in, l_out, cin, cout, k = a[3], a[4], a[5], a[6], a[7], a[10]
+                    d["flops"] += 2.0 * n * l_out * cin * cout * k
+                    d["bytes"] += esz * n * (l_in * cin + l_out * cout)
                 elif name == "dards_conv1d_bn_fwd":
                     # convolution + BatchNorm in one kernel: reads the input, writes y (kept for the backward) and, when the
                     # whole normalisation runs in the epilogue, the activation (+ reads the residual)

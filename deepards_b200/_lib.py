@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdeepards_b200.so")
 
 F32, BF16 = 0, 1
 HINT_LAST_USE = 0x100   # DARDS_HINT_LAST_USE: OR-ed into `impl` (conv fwd / dgrad) or `relu` (gbn_fwd)
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 P, I, LL, ULL, F, D = c_void_p, c_int, c_longlong, c_ulonglong, c_float, c_double
 
@@ -37,6 +37,9 @@ _SIGNATURES = {
     "dards_conv1d_dgrad": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "dards_conv1d_wgrad": [P, P, P, I, P, LL, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "dards_conv1d_wgrad_workspace_bytes": [I, I, I, I, I, I],
+    "dards_conv1d_wgrad_accum": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "dards_unpack_wgrad_batched": [P, I, I, P],
+    "dards_memset_zero": [P, LL, P],
     "dards_conv1d_bn_mode": [I, I, I, I, I, I, I, I, I, I],
     "dards_conv1d_bn_part_entries": [I, I, I, I, I, I, I, I, I],
     "dards_conv1d_bn_fwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, F, I, I, P],

@@ -36,6 +36,9 @@ int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, v
                   int n_breaths, int l_in, int l_out, int c_in, int c_out, int in_stride, int dout_stride, int ktaps,
                   int stride, int pad, cudaStream_t st);
 long long tc_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps);
+int tc_conv_wgrad_accum(const void* in, const void* dout, float* dw_t, int n_breaths, int l_in, int l_out, int c_in, int c_out,
+                        int in_stride, int dout_stride, int ktaps, int stride, int pad, cudaStream_t st);
+int simt_unpack_wgrad_batched(const dards_unpack_desc*, int, int, cudaStream_t);
 int tc_debug_set(int key, int value);
 int set_sm_limit(int n);
 int tc_conv_bn_mode(int n_breaths, int group, int l_in, int l_out, int c_in, int c_out, int ktaps, int stride, int pad);
@@ -89,7 +92,7 @@ using namespace dards;
 
 extern "C" {
 
-int dards_version(void) { return 6; }
+int dards_version(void) { return 7; }
 
 const char* dards_last_error(void) { return g_err; }
 
@@ -187,6 +190,36 @@ int dards_conv1d_wgrad(const void* in, const void* dout, float* dw, int accumula
   DARDS_CHECK_ARG(impl == 0, "conv1d_wgrad: unknown impl %d", impl);
   return simt_conv_wgrad(in, dout, dw, accumulate, workspace, workspace_bytes, n_breaths, l_in, l_out, c_in, c_out,
                          in_stride, dout_stride, ktaps, stride, pad, dtype, S(stream));
+}
+
+int dards_conv1d_wgrad_accum(const void* in, const void* dout, float* dw_t, int n_breaths, int l_in, int l_out, int c_in,
+                             int c_out, int in_stride, int dout_stride, int ktaps, int stride, int pad, int dtype,
+                             void* stream) {
+  DARDS_CHECK_ARG(in && dout && dw_t, "conv1d_wgrad_accum: null pointer");
+  DARDS_CHECK_ARG(dtype == DARDS_BF16, "conv1d_wgrad_accum: the tcgen05 path is bf16 only");
+  DARDS_CHECK_ARG(n_breaths > 0 && l_in > 0 && c_in > 0 && c_out > 0 && ktaps > 0 && stride > 0 && pad >= 0,
+                  "conv1d_wgrad_accum: bad shape");
+  DARDS_CHECK_ARG(l_out == conv_out_len(l_in, ktaps, stride, pad), "conv1d_wgrad_accum: l_out mismatch");
+  DARDS_CHECK_ARG(in_stride >= c_in && dout_stride >= c_out, "conv1d_wgrad_accum: row stride smaller than channel count");
+  return tc_conv_wgrad_accum(in, dout, dw_t, n_breaths, l_in, l_out, c_in, c_out, in_stride, dout_stride, ktaps, stride, pad,
+                             S(stream));
+}
+
+int dards_unpack_wgrad_batched(const dards_unpack_desc* descs_dev, int n_descs, int total_blocks, void* stream) {
+  DARDS_CHECK_ARG(descs_dev && n_descs >= 0 && total_blocks >= 0, "unpack_wgrad_batched: bad argument");
+  return simt_unpack_wgrad_batched(descs_dev, n_descs, total_blocks, S(stream));
+}
+
+int dards_memset_zero(void* ptr, long long bytes, void* stream) {
+  DARDS_CHECK_ARG(ptr && bytes >= 0, "memset_zero: bad argument");
+  if (bytes == 0) return DARDS_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, S(stream));
+  if (e != cudaSuccess) {
+    set_error("memset_zero: %s", cudaGetErrorString(e));
+    return DARDS_ERR_CUDA;
+  }
+  count_launch();
+  return DARDS_OK;
 }
 
 long long dards_conv1d_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps, int impl) {

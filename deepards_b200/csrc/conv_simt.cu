@@ -64,6 +64,30 @@ __global__ void __launch_bounds__(256) pack_conv_weights_batched_kernel(const da
   }
 }
 
+// The inverse for the weight GRADIENTS of the accumulate-mode tcgen05 wgrad: dw[co][ci][t] = dw_t[t][co][ci] for a whole
+// table of convolutions in one launch (one 32 x 32 x ktaps tile per block, through shared memory: both sides coalesced).
+__global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dards_unpack_desc* __restrict__ descs, int n) {
+  __shared__ dards_unpack_desc d;
+  __shared__ float tile[PACK_TILE][PACK_TILE * PACK_MAX_TAPS + 1];
+  find_block_desc(descs, n, &d);
+  const int K = d.ktaps, c_in = d.c_in, c_out = d.c_out;
+  const int n_co_t = (c_out + PACK_TILE - 1) / PACK_TILE;
+  const int b = (int)blockIdx.x - d.first_block;
+  const int co0 = (b % n_co_t) * PACK_TILE, ci0 = (b / n_co_t) * PACK_TILE;
+  for (int i = threadIdx.x; i < PACK_TILE * PACK_TILE * K; i += 256) {
+    const int a = i % PACK_TILE, bq = (i / PACK_TILE) % PACK_TILE, t = i / (PACK_TILE * PACK_TILE);
+    const int ci = ci0 + a, co = co0 + bq;   // a = ci, fastest in dw_t
+    tile[bq][a * K + t] = (ci < c_in && co < c_out) ? d.dw_t[((size_t)t * c_out + co) * c_in + ci] : 0.f;
+  }
+  __syncthreads();
+  const int row = PACK_TILE * K;  // floats of one co row inside the tile
+  for (int i = threadIdx.x; i < PACK_TILE * row; i += 256) {
+    const int co_l = i / row, rem = i % row;
+    const int co = co0 + co_l, ci = ci0 + rem / K;
+    if (co < c_out && ci < c_in) d.dw[((size_t)co * c_in + ci0) * K + rem] = tile[co_l][rem];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad implicit GEMM:  128 rows x 64 cols per CTA, BK = 16, 256 threads, 8x4 per thread
 // ------------------------------------------------------------------------------------------------
@@ -327,6 +351,13 @@ int simt_pack_conv_weights_batched(const dards_pack_desc* descs_dev, int n, int 
   if (n == 0 || total_blocks == 0) return DARDS_OK;
   DARDS_DISPATCH_DTYPE(dtype, { pack_conv_weights_batched_kernel<T><<<total_blocks, 256, 0, st>>>(descs_dev, n); })
   DARDS_CHECK_LAUNCH("pack_conv_weights_batched");
+  return DARDS_OK;
+}
+
+int simt_unpack_wgrad_batched(const dards_unpack_desc* descs_dev, int n, int total_blocks, cudaStream_t st) {
+  if (n == 0 || total_blocks == 0) return DARDS_OK;
+  unpack_wgrad_batched_kernel<<<total_blocks, 256, 0, st>>>(descs_dev, n);
+  DARDS_CHECK_LAUNCH("unpack_wgrad_batched");
   return DARDS_OK;
 }
 

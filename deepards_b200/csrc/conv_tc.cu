@@ -536,17 +536,17 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                  const cuuint32_t* box, bool swizzle128) {
+static int make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_b, const cuuint32_t* box, bool swizzle128) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return DARDS_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r,
               rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
@@ -554,6 +554,16 @@ int make_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
     return DARDS_ERR_CUDA;
   }
   return DARDS_OK;
+}
+
+int make_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                  const cuuint32_t* box, bool swizzle128) {
+  return make_map(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_b, box, swizzle128);
+}
+
+int make_f32_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                 const cuuint32_t* box, bool swizzle128) {
+  return make_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_b, box, swizzle128);
 }
 
 // SMs the persistent kernels size their grids for.  dards_set_sm_limit(n) (data-parallel runs) leaves a few SMs to the

@@ -112,6 +112,13 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, uint32_t
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// out[tile] += smem tile, 3-D map (fp32 wgrad accumulation: the adds happen at the L2, in arrival order)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // all but the most recent bulk group have finished reading their shared-memory source
@@ -200,6 +207,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t lbo
 // bf16 tensor map with zero fill out of bounds.  dims / box innermost first; strides in BYTES for dims 1..rank-1.
 int make_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
                   const cuuint32_t* box, bool swizzle128);
+// the same for fp32 elements (the accumulate-mode wgrad epilogue: 32-float rows = one 128-byte swizzle row)
+int make_f32_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                 const cuuint32_t* box, bool swizzle128);
 int sm_count();
 
 }  // namespace dards

@@ -23,6 +23,8 @@
 // Tile: 128 output channels (TMEM lanes) x up to 128 input channels (columns) x up to 3 taps (3 accumulators =
 // 384 TMEM columns).  Split-K over groups of breaths; every CTA writes its fp32 partial tile and a second kernel
 // reduces the partials in a fixed order (deterministic) into the parameter's (Cout, Cin, K) layout.
+#include <cstring>
+
 #include "tc_common.cuh"
 
 namespace dards {
@@ -56,11 +58,12 @@ struct WgTcParams {
   int fuse_taps;               // 1: the 3 taps are the 3 column chunks of one N = 192 MMA (c_in == 64, stride 1)
   int tap_cols;                // TMEM column distance between the taps' accumulators (128, or 64 when fused)
   int l2_hint;                 // 1: the saved input activations (their last use) are loaded with L2 evict_first priority
+  int accumulate_l2;           // 1: the CTA's tile is ADDED into dw_t[t][co][ci] with TMA reduce-add (no partials, no reduce kernel)
 };
 
 __global__ void __launch_bounds__(WG_TC_THREADS, 1)
     tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    float* __restrict__ partial, const WgTcParams p) {
+                    const __grid_constant__ CUtensorMap tm_d, float* __restrict__ partial, const WgTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -207,6 +210,44 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
         }
       }
       if (issuer) umma_commit(done_bar);
+    }
+  } else if (p.accumulate_l2) {
+    // epilogue, accumulate mode: the fp32 tile of every tap goes through shared memory (the operand ring is idle once the
+    // last MMA has completed) as 128 x 32 sub-tiles in the TMA's SWIZZLE_128B layout -- thread = output channel = row, its
+    // 16-byte chunk j lands at chunk j ^ (row & 7), so the 32 rows of a warp spread over all banks -- and is ADDED into
+    // dw_t[t][co][ci] by cp.reduce.async.bulk at the L2.  143 CTAs x 196 KB of split-K partials no longer travel to HBM and
+    // back, and there is no reduce kernel; the order of the fp32 additions is the arrival order (not bit-reproducible).
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
+    if (n_iters > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const int n_sub = ci_n / 32;
+      for (int t = 0; t < p.n_taps; ++t) {
+        if (t > 0) {
+          if (leader) tma_store_wait_read();          // the previous tap's reduce operations have read the staging tiles
+          named_bar_sync(1, 128);
+        }
+        for (int sb = 0; sb < n_sub; ++sb) {
+          uint32_t v[32];
+          tmem_ld16(t_row + (uint32_t)(t * p.tap_cols + sb * 32), *reinterpret_cast<uint32_t(*)[16]>(v));
+          tmem_ld16(t_row + (uint32_t)(t * p.tap_cols + sb * 32 + 16), *reinterpret_cast<uint32_t(*)[16]>(v + 16));
+          tmem_ld_wait();
+          uint8_t* tile = smem_gen + sb * 16384 + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(tile + ((j ^ (row & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (leader) {
+          for (int sb = 0; sb < n_sub; ++sb) tma_reduce_add_3d(&tm_d, smem_base + sb * 16384, ci0 + sb * 32, co0, t);
+          tma_store_commit();
+        }
+      }
+      if (leader) tma_store_wait_all();
     }
   } else {
     // epilogue: partial[split][t][co][ci] (fp32); thread = output channel, 16 input channels per TMEM load
@@ -361,6 +402,26 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   return w;
 }
 
+static int wg_launch(WgPlan& w, const void* in, const void* dout, float* partial, float* dw_t, int n_breaths, int l_in,
+                     int l_out, int c_in, int c_out, int in_stride, int dout_stride, int ktaps, int stride, cudaStream_t st);
+
+// dw_t[t][co][ci] += ... : accumulate mode (the buffer must be zeroed by the caller once per backward pass)
+int tc_conv_wgrad_accum(const void* in, const void* dout, float* dw_t, int n_breaths, int l_in, int l_out, int c_in, int c_out,
+                        int in_stride, int dout_stride, int ktaps, int stride, int pad, cudaStream_t st) {
+  WgPlan w = wg_plan(n_breaths, l_in, l_out, c_in, c_out, ktaps, stride, pad);
+  if (!w.ok) {
+    set_error("tcgen05 wgrad: unsupported shape (k=%d s=%d p=%d cin=%d cout=%d l=%d)", ktaps, stride, pad, c_in, c_out, l_in);
+    return DARDS_ERR_UNSUPPORTED;
+  }
+  DARDS_CHECK_ARG(in_stride % 8 == 0 && dout_stride % 8 == 0, "tcgen05 wgrad: row strides must be multiples of 8");
+  DARDS_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dw_t) & 15) == 0,
+                  "tcgen05 wgrad: operands must be 16-byte aligned");
+  DARDS_CHECK_ARG(c_in % 32 == 0, "tcgen05 wgrad (accumulate): input channels must be a multiple of 32");
+  w.p.accumulate_l2 = 1;
+  return wg_launch(w, in, dout, nullptr, dw_t, n_breaths, l_in, l_out, c_in, c_out, in_stride, dout_stride, ktaps, stride, st);
+}
+
 long long tc_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps) {
   // the split count does not depend on stride/pad beyond validity; use the stride-1 plan shape
   WgPlan w = wg_plan(n_breaths, l_out, l_out, c_in, c_out, ktaps, 1, ktaps == 3 ? 1 : 0);
@@ -368,22 +429,19 @@ long long tc_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out
   return (long long)w.splits * ktaps * c_in * c_out * (long long)sizeof(float);
 }
 
-int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, void* workspace, long long workspace_bytes,
-                  int n_breaths, int l_in, int l_out, int c_in, int c_out, int in_stride, int dout_stride, int ktaps,
-                  int stride, int pad, cudaStream_t st) {
-  WgPlan w = wg_plan(n_breaths, l_in, l_out, c_in, c_out, ktaps, stride, pad);
-  if (!w.ok) {
-    set_error("tcgen05 wgrad: unsupported shape (k=%d s=%d p=%d cin=%d cout=%d l=%d)", ktaps, stride, pad, c_in, c_out, l_in);
-    return DARDS_ERR_UNSUPPORTED;
-  }
-  DARDS_CHECK_ARG(in_stride % 8 == 0 && dout_stride % 8 == 0, "tcgen05 wgrad: row strides must be multiples of 8");
-  DARDS_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0,
-                  "tcgen05 wgrad: operands must be 16-byte aligned");
-  const long long need = (long long)w.splits * ktaps * c_in * c_out * (long long)sizeof(float);
-  DARDS_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "tcgen05 wgrad: workspace too small (%lld < %lld)",
-                  workspace_bytes, need);
+static int wg_launch(WgPlan& w, const void* in, const void* dout, float* partial, float* dw_t, int n_breaths, int l_in,
+                     int l_out, int c_in, int c_out, int in_stride, int dout_stride, int ktaps, int stride, cudaStream_t st) {
   WgTcParams& p = w.p;
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_d;
+  if (dw_t) {
+    cuuint64_t dims[3] = {(cuuint64_t)c_in, (cuuint64_t)c_out, (cuuint64_t)ktaps};
+    cuuint64_t str[2] = {(cuuint64_t)c_in * 4, (cuuint64_t)c_in * c_out * 4};
+    cuuint32_t box[3] = {32, 128, 1};
+    int rc = make_f32_map(&tm_d, dw_t, 3, dims, str, box, true);
+    if (rc) return rc;
+  } else {
+    memset(&tm_d, 0, sizeof(tm_d));
+  }
   {
     cuuint64_t dims[4] = {(cuuint64_t)c_out, 1, (cuuint64_t)l_out, (cuuint64_t)n_breaths};
     cuuint64_t str[3] = {(cuuint64_t)dout_stride * 2, (cuuint64_t)dout_stride * 2, (cuuint64_t)dout_stride * l_out * 2};
@@ -410,8 +468,30 @@ int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, v
     attr_smem = smem;
   }
   dim3 grid(p.n_ci_tiles * p.n_co_tiles, w.splits);
-  tc_wgrad_kernel<<<grid, WG_TC_THREADS, smem, st>>>(tm_a, tm_b, static_cast<float*>(workspace), p);
+  tc_wgrad_kernel<<<grid, WG_TC_THREADS, smem, st>>>(tm_a, tm_b, tm_d, partial, p);
   DARDS_CHECK_LAUNCH("tc_wgrad");
+  return DARDS_OK;
+}
+
+
+int tc_conv_wgrad(const void* in, const void* dout, float* dw, int accumulate, void* workspace, long long workspace_bytes,
+                  int n_breaths, int l_in, int l_out, int c_in, int c_out, int in_stride, int dout_stride, int ktaps,
+                  int stride, int pad, cudaStream_t st) {
+  WgPlan w = wg_plan(n_breaths, l_in, l_out, c_in, c_out, ktaps, stride, pad);
+  if (!w.ok) {
+    set_error("tcgen05 wgrad: unsupported shape (k=%d s=%d p=%d cin=%d cout=%d l=%d)", ktaps, stride, pad, c_in, c_out, l_in);
+    return DARDS_ERR_UNSUPPORTED;
+  }
+  DARDS_CHECK_ARG(in_stride % 8 == 0 && dout_stride % 8 == 0, "tcgen05 wgrad: row strides must be multiples of 8");
+  DARDS_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0,
+                  "tcgen05 wgrad: operands must be 16-byte aligned");
+  const long long need = (long long)w.splits * ktaps * c_in * c_out * (long long)sizeof(float);
+  DARDS_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "tcgen05 wgrad: workspace too small (%lld < %lld)",
+                  workspace_bytes, need);
+  w.p.accumulate_l2 = 0;
+  int rc = wg_launch(w, in, dout, static_cast<float*>(workspace), nullptr, n_breaths, l_in, l_out, c_in, c_out, in_stride,
+                     dout_stride, ktaps, stride, st);
+  if (rc) return rc;
   const int per = ktaps * c_in * c_out;
   const float* part = static_cast<const float*>(workspace);
   if (w.splits <= 16)

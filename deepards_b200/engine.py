@@ -70,7 +70,7 @@ class Recorder(object):
 
 
 class _ConvRec(object):
-    __slots__ = ("mod", "cin", "cout", "k", "stride", "pad", "kio", "koi", "goff")
+    __slots__ = ("mod", "cin", "cout", "k", "stride", "pad", "kio", "koi", "goff", "dwt")
 
 
 class Plan(object):
@@ -126,6 +126,17 @@ class Plan(object):
         # [0] forward counter (fresh dropout masks per step), [1] global index of this rank's first sequence
         self.seed_dev = self.new((2,), torch.int64, zero=True)
         self._seq_offset = 0
+        # tcgen05 weight gradients: "accumulate" (default) adds every CTA's fp32 tile into a tap-major buffer at the L2 (no
+        # split-K partials, no reduce kernels; fp32 summation order = arrival order), "deterministic" keeps the split-K
+        # partials + fixed-order reduce kernels (bit-reproducible)
+        self.wgrad_mode = os.environ.get("DEEPARDS_B200_WGRAD", "accumulate")
+        self._dwt_arena = None
+        self._dwt_used = 0
+        self._pending_unpack = []
+        if not self.simt_only and self.wgrad_mode == "accumulate":
+            import torch.nn as nn
+            total = sum((m.weight.numel() + 3) // 4 * 4 for m in backbone.modules() if isinstance(m, nn.Conv1d))
+            self._dwt_arena = self.new((max(total, 4),), torch.float32, zero=True)
         self._running = []   # (mean, rstd, bn, rows, c): running-statistics updates, one batched launch per forward
         self._pending_red = []  # (partial table, rows, c, destination pointer): flushed as one batched launch
         kind = backbone.network_name
@@ -137,6 +148,9 @@ class Plan(object):
             raise NotImplementedError(kind)
         self._flush_running()
         self._flush_reductions()
+        if self._dwt_arena is not None and self._dwt_used:
+            # zeroed at the end of every forward: the backward's weight-gradient kernels add into it
+            self.fwd.add("dards_memset_zero", self._dwt_arena.data_ptr(), 4 * self._dwt_used)
         self._build_pack_table()
 
     # ------------------------------------------------------------------------------------------------------
@@ -191,6 +205,7 @@ class Plan(object):
         c.stride, c.pad = mod.stride[0], mod.padding[0]
         c.kio = self.new((c.k, c.cin, c.cout))
         c.koi = self.new((c.k, c.cout, c.cin))
+        c.dwt = None
         self.convs.append(c)
         return c
 
@@ -227,6 +242,15 @@ class Plan(object):
     def conv_wgrad(self, c, src, src_stride, dout, dout_stride, l_in):
         l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
         tc = self._tc_ok(c, "wgrad")
+        if tc and self._dwt_arena is not None and c.cin % 32 == 0:
+            if c.dwt is None:
+                n = c.k * c.cout * c.cin
+                c.dwt = self._dwt_arena[self._dwt_used:self._dwt_used + n]
+                self._dwt_used += (n + 3) // 4 * 4
+            self.bwd.add("dards_conv1d_wgrad_accum", src, dout, c.dwt.data_ptr(), self.N, l_in, l_out, c.cin, c.cout,
+                         src_stride, dout_stride, c.k, c.stride, c.pad, self.dt)
+            self._pending_unpack.append((c, self.gptr(c.mod.weight)))
+            return
         impl = 1 if tc else 0
         need = _lib.fn("dards_conv1d_wgrad_workspace_bytes")(self.N, l_out, c.cin, c.cout, c.k, impl)
         ws = self._wgrad_ws(need)
@@ -353,9 +377,28 @@ class Plan(object):
         self.fwd.add("dards_bn_running_update_batched", t.data_ptr(), len(self._running), first, BN_EPS)
         self._running = []
 
+    def _flush_unpack(self):
+        """Tap-major accumulation buffers of the weight gradients computed since the last flush -> the parameters'
+        (Cout, Cin, K) gradient slots, in one launch."""
+        if not self._pending_unpack:
+            return
+        import numpy as np
+        dt = np.dtype([("dw_t", "<u8"), ("dw", "<u8"), ("c_out", "<i4"), ("c_in", "<i4"), ("ktaps", "<i4"),
+                       ("first_block", "<i4")])
+        tab = np.zeros(len(self._pending_unpack), dtype=dt)
+        first = 0
+        for i, (c, dst) in enumerate(self._pending_unpack):
+            tab[i] = (c.dwt.data_ptr(), dst, c.cout, c.cin, c.k, first)
+            first += ((c.cout + 31) // 32) * ((c.cin + 31) // 32)
+        t = torch.from_numpy(tab.view(np.uint8).copy()).to(self.device)
+        self.bufs.append(t)
+        self.bwd.add("dards_unpack_wgrad_batched", t.data_ptr(), len(self._pending_unpack), first)
+        self._pending_unpack = []
+
     def _flush_reductions(self):
         """Per-group partial sums (BatchNorm dgamma/dbeta, stem dW) accumulated since the last flush -> their gradient
         slots, in one launch."""
+        self._flush_unpack()
         if not self._pending_red:
             return
         import numpy as np

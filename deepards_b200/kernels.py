@@ -74,6 +74,25 @@ def conv1d_wgrad(x, dout, k, stride, pad, impl=0):
     return dw
 
 
+def conv1d_wgrad_accum(x, dout, k, stride, pad):
+    """tcgen05 weight gradient through the accumulate path: zeroed tap-major buffer, L2 reduce-adds, one unpack launch."""
+    import numpy as np
+    n, l, cin = x.shape
+    _, lo, cout = dout.shape
+    dwt = torch.zeros((k, cout, cin), dtype=torch.float32, device=x.device)
+    dw = torch.empty((cout, cin, k), dtype=torch.float32, device=x.device)
+    _lib.call("dards_memset_zero", dwt.data_ptr(), dwt.numel() * 4, _st(x))
+    _lib.call("dards_conv1d_wgrad_accum", x.data_ptr(), dout.data_ptr(), dwt.data_ptr(), n, l, lo, cin, cout, _rowstride(x),
+              _rowstride(dout), k, stride, pad, _dt(x), _st(x))
+    dt = np.dtype([("dw_t", "<u8"), ("dw", "<u8"), ("c_out", "<i4"), ("c_in", "<i4"), ("ktaps", "<i4"), ("first_block", "<i4")])
+    tab = np.zeros(1, dtype=dt)
+    tab[0] = (dwt.data_ptr(), dw.data_ptr(), cout, cin, k, 0)
+    t = torch.from_numpy(tab.view(np.uint8).copy()).to(x.device)
+    _lib.call("dards_unpack_wgrad_batched", t.data_ptr(), 1, ((cout + 31) // 32) * ((cin + 31) // 32), _st(x))
+    torch.cuda.synchronize()
+    return dw
+
+
 def conv1d_bn_fwd(x, w, gamma, beta, group, stride, pad, relu, res=None, eps=1e-5, ds=None):
     """conv -> grouped BatchNorm (+ res) (+ ReLU) through the fused tcgen05 kernel (bf16 only).
     x (N, L, Cin) channels-last bf16; returns (mode, y, out, mean, rstd, extra).  mode 2: one kernel; mode 1: convolution with

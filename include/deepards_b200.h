@@ -109,6 +109,25 @@ int dards_conv1d_wgrad(const void* in, const void* dout, float* dw, int accumula
                        void* stream);
 long long dards_conv1d_wgrad_workspace_bytes(int n_breaths, int l_out, int c_in, int c_out, int ktaps, int impl);
 
+/* Accumulate-mode weight gradient (tcgen05, bf16): dw_t[t][co][ci] += sum_{n,q} dout * in -- fp32, TAP-major, added into
+ * the buffer by TMA reduce operations at the L2.  No split-K partials travel to memory and no reduce kernel runs (the
+ * deterministic entry point above writes and re-reads ~28 MB per layer at the BASELINE shapes); the price is that the
+ * order of the fp32 additions is the CTAs' arrival order, so results are not bit-reproducible from run to run.  The
+ * caller zeroes dw_t once per backward pass (dards_memset_zero) and converts all layers to the parameter layout
+ * (Cout, Cin, K) with ONE dards_unpack_wgrad_batched launch.  c_in % 32 == 0. */
+int dards_conv1d_wgrad_accum(const void* in, const void* dout, float* dw_t, int n_breaths, int l_in, int l_out, int c_in,
+                             int c_out, int in_stride, int dout_stride, int ktaps, int stride, int pad, int dtype,
+                             void* stream);
+typedef struct dards_unpack_desc {
+  const float* dw_t; /* [ktaps][c_out][c_in] */
+  float* dw;         /* [c_out][c_in][ktaps], the nn.Conv1d weight layout */
+  int c_out, c_in, ktaps, first_block;
+} dards_unpack_desc;
+/* descriptor j owns ceil(c_out/32) * ceil(c_in/32) blocks starting at first_block_j; ktaps <= 8 */
+int dards_unpack_wgrad_batched(const dards_unpack_desc* descs_dev, int n_descs, int total_blocks, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream (capturable; the accumulation buffers of a backward pass) */
+int dards_memset_zero(void* ptr, long long bytes, void* stream);
+
 /* ---- convolution with the BatchNorm that follows it, in one kernel (tcgen05, bf16) -------------- */
 /* conv -> bn -> relu [-> += residual -> relu] (resnet.py:27-38) and conv -> norm -> relu (densenet.py:25-29):
  * y = conv(in) is stored (the backward needs it); its per-group statistics are taken from the fp32 accumulators in

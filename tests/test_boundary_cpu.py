@@ -25,7 +25,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "library does not export %s" % name
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes binding and header disagree"
-    assert lib.dards_version() == _lib.ABI_VERSION == 6
+    assert lib.dards_version() == _lib.ABI_VERSION == 7
     # the shared object is self-contained: it must not need libcuda / libcudart at load time
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out and "libcudart" not in out

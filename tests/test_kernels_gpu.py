@@ -235,6 +235,21 @@ def test_conv_tcgen05_wgrad(case):
     assert torch.equal(got, K().conv1d_wgrad(xb, dyb, k, s, p, impl=1))  # deterministic (fixed-order split-K reduction)
 
 
+@pytest.mark.parametrize("case", [(40, 64, 64, 56, 3, 1, 1), (40, 64, 128, 56, 3, 2, 1), (40, 64, 128, 56, 1, 2, 0),
+                                  (300, 128, 128, 28, 3, 1, 1), (23, 256, 512, 14, 3, 2, 1), (333, 512, 512, 7, 3, 1, 1),
+                                  (60, 96, 128, 28, 1, 1, 0), (60, 128, 32, 14, 3, 1, 1), (5120, 256, 256, 14, 3, 1, 1)])
+def test_conv_tcgen05_wgrad_accumulate_mode(case):
+    """The accumulate path (TMA reduce-add of every CTA's fp32 tile into a tap-major buffer at the L2 + one unpack launch)
+    against the deterministic split-K path: same products, fp32 additions in a different (arrival) order."""
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 13)
+    xb, dyb = cl(x.bfloat16()), cl(dy.bfloat16())
+    ref = K().conv1d_wgrad(xb, dyb, k, s, p, impl=1)
+    got = K().conv1d_wgrad_accum(xb, dyb, k, s, p)
+    assert rel_err(got, ref) < 1e-5, rel_err(got, ref)
+    assert rel_err(got, K().conv1d_wgrad(xb, dyb, k, s, p, impl=0)) < 2e-4
+
+
 @pytest.mark.parametrize("case", [(40, 64, 64, 56, 3, 1, 1), (333, 64, 128, 28, 3, 1, 1), (2000, 64, 32, 7, 3, 1, 1)])
 def test_conv_tcgen05_wgrad_fused_taps(case):
     """64 input channels: the three taps issued as ONE N = 192 MMA (descriptor chunk stride = one row) accumulate the
