@@ -253,7 +253,16 @@ def test_transformer_head_matches_reference():
     assert rel_err(out.detach().cpu(), z["logits"]) <= FP32_TOL
     assert abs(float(loss) - float(z["loss"])) <= FP32_TOL
     grads = {n: p.grad for n, p in net.named_parameters()}
-    worst = max(rel_err(grads[k[5:]].cpu(), z[k]) for k in z.files if k.startswith("grad/"))
+    # the key projection's bias has a mathematically ZERO gradient (a constant added to every key shifts each softmax row
+    # uniformly): what both sides hold there is rounding noise, so every tensor is measured against at least 1e-3 of the
+    # largest gradient entry of the head
+    gkeys = [k for k in z.files if k.startswith("grad/")]
+    gmax = max(float(abs(z[k]).max()) for k in gkeys)
+    worst = 0.0
+    for k in gkeys:
+        ref = torch.from_numpy(z[k])
+        err = float((grads[k[5:]].cpu() - ref).abs().max()) / max(float(ref.abs().max()), 1e-3 * gmax)
+        worst = max(worst, err)
     print("transformer head: worst gradient rel err %.2e" % worst)
     assert worst <= 5 * FP32_TOL      # through two LayerNorm + softmax blocks; the backbone gradients are held to 1e-4 elsewhere
 

@@ -40,7 +40,9 @@ def short(name):
 
 
 # bench.py's names for the C entry points (the keys of profiles/traffic.json)
-ENTRY = [('gbn_bwd', 'dards_gbn_bwd'), ('gbn_fwd', 'dards_gbn_fwd'), ('tc_wgrad_kernel', 'dards_conv1d_wgrad:tcgen05'),
+ENTRY = [('gbn_bwd', 'dards_gbn_bwd'), ('gbn_fwd', 'dards_gbn_fwd'), ('gbn_apply', 'dards_gbn_apply_fwd'),
+         ('tc_conv_bn', 'dards_conv1d_bn_fwd'), ('tc_wgrad_kernel', 'dards_conv1d_wgrad_accum'),
+         ('unpack_wgrad', 'dards_unpack_wgrad_batched'),
          ('tc_wgrad_reduce', 'wgrad_reduce'), ('tc_conv', 'dards_conv1d:tcgen05'), ('stem_fwd', 'dards_stem_fwd'), ('stem_bwd', 'dards_stem_bwd'),
          ('dropout', 'dards_dropout')]
 
