@@ -201,7 +201,8 @@ def run_b200(args):
     if world > 1:
         # the all-reduces overlap the backward pass: keep NCCL to a few CTAs (the trainer sizes the persistent kernels'
         # grids for the SMs that are left, DEEPARDS_B200_DP_SM_RESERVE)
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
+        if os.environ.get("DEEPARDS_B200_NCCL_CHANNELS"):
+            os.environ["NCCL_MAX_NCHANNELS"] = os.environ["DEEPARDS_B200_NCCL_CHANNELS"]
         # NCCL prints its version banner on stdout at init; the contract is ONE JSON line there
         sys.stdout.flush()
         saved = os.dup(1)

@@ -28,9 +28,14 @@ SEQ_LEN = 224
 
 _DTYPES = {"fp32": (torch.float32, _lib.F32), "bf16": (torch.bfloat16, _lib.BF16)}
 
-# Smallest gradient suffix (fp32 elements) worth an all-reduce bucket of its own: 1 MB, the trainer's default bucket size.
-# ResNet-18: layer4.1 | layer4.0 | layer3.1 | layer3.0 | the rest (1.2 MB: the only all-reduce + update on the step's tail).
-DP_MARK_ELEMS = int(os.environ.get("DEEPARDS_B200_DP_BUCKET_ELEMS", 1 << 18))
+# Smallest gradient suffix (fp32 elements) worth an all-reduce bucket of its own.  Default: effectively infinite, i.e. ONE
+# bucket reduced after the backward pass.  Measured on 8 x B200 (profiles/r02_bench8_*): overlapping the reduction with the
+# backward in 5 buckets costs MORE than it hides -- every mark is a flush of the pending partial-sum / weight-gradient
+# launches plus a CUDA-graph boundary (+0.13 ms per step at 2 GPUs with the collective switched off), the NCCL kernels
+# take SMs from persistent kernels that were sized for all of them, and the whole 15.5 MB all-reduce is only ~0.1 ms
+# over NVSwitch: 2.850 ms (5 buckets, 8 SMs reserved) vs 2.728 ms (one bucket) per ResNet-18 step.  Set
+# DEEPARDS_B200_DP_BUCKET_ELEMS=262144 to get the overlapped schedule (layer4.1 | layer4.0 | layer3.1 | layer3.0 | rest).
+DP_MARK_ELEMS = int(os.environ.get("DEEPARDS_B200_DP_BUCKET_ELEMS", 1 << 30))
 
 
 def _multi_rank():

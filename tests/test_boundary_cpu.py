@@ -260,13 +260,14 @@ def test_data_parallel_marks_are_bucket_sized():
     at least one 1 MB bucket of gradients has become final; the trainer's buckets are cut at marks only.  The LAST bucket
     (all-reduce + optimizer update on the step's tail, nothing left to overlap them with) stays small."""
     from deepards_b200 import data_parallel as dp, engine
-    assert engine.DP_MARK_ELEMS == 1 << 18
+    assert engine.DP_MARK_ELEMS == 1 << 30      # default: one bucket after the backward (measured faster on NVSwitch)
+    mark_elems = 1 << 18                         # the overlapped schedule (DEEPARDS_B200_DP_BUCKET_ELEMS=262144)
     # ResNet-18 slot offsets of the first parameter of each block, last block first (3.89 M elements in total)
     total = 3_893_378
     offs = [2_318_000, 1_006_000, 612_000, 283_000, 185_000, 103_000, 78_000, 53_000]
     marks, last = [], total
     for off in offs:                       # the rule of Plan.mark
-        if last - off >= engine.DP_MARK_ELEMS:
+        if last - off >= mark_elems:
             marks.append(off)
             last = off
     assert marks == [2_318_000, 1_006_000, 612_000, 283_000]
