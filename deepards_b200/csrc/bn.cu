@@ -11,7 +11,8 @@
 //    (1120,32) (560,32) (280,64) (140,128) all give 9 rows per thread and a 72 KB tile per tensor.
 //  * streaming (generic fallback for tiles that do not fit): re-reads the tile from L1/L2 for every sweep.
 //
-// Statistics use the two-sweep (mean, then centred sum of squares) formulation for fp32-faithful variance.
+// Statistics: the cached kernels use ONE sweep of sums shifted by a sample of the data (the group's first row), which loses
+// no digits in E[d^2] - E[d]^2; the streaming fallback uses two sweeps (mean, then centred sum of squares).
 // Cross-group reductions (running statistics, dgamma/dbeta) are separate BATCHED kernels: one launch handles a
 // whole table of BatchNorm layers (an in-kernel "last CTA reduces" variant was measured 12-19 us slower per launch:
 // the gpu-scope fence of every CTA invalidates L1 and waits for its stores).

@@ -177,6 +177,11 @@ class DataParallelTrainer(object):
         mode = "per_breath" if isinstance(net, CNNSingleBreathLinearNetwork) else "cnn_linear"
         n = x.numel() // engine.SEQ_LEN
         training = bb.training
+        if not training and bb.network_name.startswith("resnet"):
+            # the same guard as the autograd path (autograd.run_plan): eval() on the reference ResNet normalises with the
+            # running statistics, which this backend does not implement -- never silently a different function
+            raise NotImplementedError("deepards_b200 ResNet implements training-mode BatchNorm (batch statistics) only; "
+                                      "keep the module in train() mode as train_ards_detector.py does")
         from .autograd import module_precision
         plan = engine.get_plan(net, bb, net.linear_final, n, x.shape[1], module_precision(net), mode,
                                dropout=_drop_key(bb) if training else (), update_running=training)
@@ -206,6 +211,13 @@ class DataParallelTrainer(object):
         plan = self.plan_for(x)
         # dlogits carries world * B_local / B_global, the update 1 / world: together the global-mean weighting
         gs = 1.0 if global_batch is None else self.world * x.shape[0] / float(global_batch)
+        # lr / momentum / weight decay / clip are kernel arguments, i.e. constants of a captured CUDA graph: when the caller
+        # changes one (lr decay, warm-up) the captured graphs are dropped and re-captured with the new values
+        hp = (self.lr, self.momentum, self.weight_decay, self.clip)
+        if plan.__dict__.setdefault("_dp_hp", hp) != hp:
+            plan.__dict__.pop("_dp_graph", None)
+            plan.__dict__.pop("_dp_seg", None)
+            plan._dp_hp = hp
         if plan.__dict__.setdefault("_dp_grad_scale", gs) != gs:
             raise RuntimeError("deepards_b200: this plan (%d sequences per rank) was first used with a different global "
                                "batch size; the loss scale is part of its captured CUDA graphs" % x.shape[0])

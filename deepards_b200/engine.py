@@ -861,7 +861,9 @@ class Plan(object):
 def get_plan(net, backbone, linear, n_breaths, group, precision, mode, dropout, update_running):
     """Plan cache on the owning module (invalidated when a parameter's storage moves)."""
     cache = net.__dict__.setdefault("_dards_plans", {})
-    key = (n_breaths, group, precision, mode, tuple(dropout), bool(update_running))
+    # multi-rank plans flush their pending partial-sum reductions at every all-reduce mark: a plan built before
+    # init_process_group() must not be reused afterwards
+    key = (n_breaths, group, precision, mode, tuple(dropout), bool(update_running), _multi_rank())
     plan = cache.get(key)
     if plan is None or not plan.valid():
         plan = Plan(net, backbone, linear, n_breaths, group, precision, mode, dropout, update_running)

@@ -94,3 +94,22 @@ def test_inference_sweep_padded_single_breath_classifier(backbone):
         if precision == "fp32":
             ref = O.cnn_linear_forward(sd, x[100:104], per_breath=True)
             assert rel_err(small.cpu(), ref) <= 1e-4
+
+
+def test_changing_the_learning_rate_after_graph_capture_takes_effect():
+    """lr is an argument of the fused optimizer kernel, i.e. a constant of the captured CUDA graph; changing
+    `trainer.lr` (decay, warm-up) must re-capture instead of being silently ignored.  Graph replay == eager, bit for bit."""
+    from deepards_b200.data_parallel import DataParallelTrainer
+    sd0 = O.cnn_linear_state("densenet18", seed=33, bn_perturb=0.1)
+    x, t = O.synthetic_breaths(4, seed=210).cuda(), O.synthetic_targets(4, seed=210).cuda()
+    out = {}
+    for use_graph in (False, True):
+        net = _net("densenet18", {k: v.clone() for k, v in sd0.items()}, "bf16")
+        tr = DataParallelTrainer(net, lr=1e-3, optimizer="sgd", weight_decay=1e-4, clip_val=0.01, use_graph=use_graph)
+        for i in range(8):
+            if i == 5:
+                tr.lr = 1e-2        # after the graph has been captured (third call)
+            tr.train_step(x, t)
+        torch.cuda.synchronize()
+        out[use_graph] = tr.param_flat.clone()
+    assert torch.equal(out[False], out[True])
