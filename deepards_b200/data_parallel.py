@@ -208,6 +208,10 @@ class DataParallelTrainer(object):
         return self._train_step(raw, target, (mu, std, padded), global_batch)
 
     def _train_step(self, x, target, scaling, global_batch=None):
+        with engine.nvtx_range("deepards_b200.train_step"):
+            return self._train_step_impl(x, target, scaling, global_batch)
+
+    def _train_step_impl(self, x, target, scaling, global_batch=None):
         plan = self.plan_for(x)
         # dlogits carries world * B_local / B_global, the update 1 / world: together the global-mean weighting
         gs = 1.0 if global_batch is None else self.world * x.shape[0] / float(global_batch)

@@ -55,6 +55,26 @@ def _conv_impl_override():
     return os.environ.get("DEEPARDS_B200_CONV_IMPL", "")  # "simt" forces the CUDA-core kernels everywhere
 
 
+NVTX = int(os.environ.get("DEEPARDS_B200_NVTX", "0"))   # 1: a range per phase (forward / backward / update); 2: + per call
+
+
+class nvtx_range(object):
+    """`with nvtx_range("forward"):` -- an NVTX range when DEEPARDS_B200_NVTX is set, nothing otherwise (SURVEY.md section
+    5: tracing; the ranges show up in Nsight Systems / Compute timelines around the recorded kernel lists)."""
+
+    def __init__(self, name, level=1):
+        self.on = NVTX >= level
+        self.name = name
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+
+
 class Recorder(object):
     """A replayable list of C-ABI calls."""
 
@@ -65,6 +85,13 @@ class Recorder(object):
         self.calls.append((name, _lib.fn(name), args))
 
     def run(self, stream):
+        if NVTX >= 2:
+            for name, f, args in self.calls:
+                with nvtx_range(name, 2):
+                    rc = f(*args, stream)
+                if rc != 0:
+                    _lib.check(rc, name)
+            return
         for name, f, args in self.calls:
             rc = f(*args, stream)
             if rc != 0:
@@ -821,22 +848,24 @@ class Plan(object):
             self.pack.run(st)
             self.fwd.run(st)
 
-        g = self._graph_for("fwd", run)
-        if g is not None:
-            g.replay()
-        else:
-            run(self._stream())
+        with nvtx_range("deepards_b200.forward"):
+            g = self._graph_for("fwd", run)
+            if g is not None:
+                g.replay()
+            else:
+                run(self._stream())
         self.fwd_serial += 1
 
     def run_backward(self):
         if self.bwd_serial == self.fwd_serial:
             raise RuntimeError("backward() without a new forward(): forward #%d has already been back-propagated "
                                "(in-place backward kernels consumed its buffers)" % self.fwd_serial)
-        g = self._graph_for("bwd", self.bwd.run)
-        if g is not None:
-            g.replay()
-        else:
-            self.bwd.run(self._stream())
+        with nvtx_range("deepards_b200.backward"):
+            g = self._graph_for("bwd", self.bwd.run)
+            if g is not None:
+                g.replay()
+            else:
+                self.bwd.run(self._stream())
         self.bwd_serial = self.fwd_serial
 
     def mark_no_backward(self):
