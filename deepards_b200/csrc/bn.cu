@@ -746,9 +746,22 @@ static const BnCfg kBnCfgs[] = {{256, 16}, {256, 8}, {256, 4}, {512, 4}};
 constexpr int BN_MAX_K = 9;                 // rows per thread (bounds the cache: 9 * threads * 16 B per tensor)
 constexpr int BN_CACHE_LIMIT = 222 * 1024;  // dynamic shared memory we are willing to ask for (3 x 72 KB tiles fit)
 
+int g_dbg_bn_shift = -1;  // debug key 15 = s: skip the s widest tile configurations that would fit (narrower tiles, more of them)
+int g_dbg_bn_k = -1;      // debug key 16 = 1: resident CTAs per SM chosen for the fullest last wave instead of the maximum
+
 // picks a configuration whose tile holds the whole group; -1 -> use the streaming kernels
+static int bn_pick_cfg_from(int first, int rows, int c, int v, int tensors);
 static int bn_pick_cfg(int rows, int c, int v, int tensors) {
-  for (int i = 0; i < 4; ++i) {
+  int cfg = bn_pick_cfg_from(0, rows, c, v, tensors);
+  for (int s = 0; s < g_dbg_bn_shift && cfg >= 0; ++s) {
+    const int narrower = bn_pick_cfg_from(cfg + 1, rows, c, v, tensors);
+    if (narrower < 0) break;
+    cfg = narrower;
+  }
+  return cfg;
+}
+static int bn_pick_cfg_from(int first, int rows, int c, int v, int tensors) {
+  for (int i = first; i < 4; ++i) {
     const int lanes = kBnCfgs[i].threads / kBnCfgs[i].vpr;
     const int k = ceil_div(rows, lanes);
     if (k > BN_MAX_K) continue;
@@ -779,6 +792,18 @@ static int bn_persistent_grid(size_t smem_dyn, size_t smem_static, int threads, 
   if (per_sm > 4) per_sm = 4;
   if (per_sm * threads > 2048) per_sm = 2048 / threads;
   if (per_sm < 1) per_sm = 1;
+  if (g_dbg_bn_k == 1 && per_sm > 2) {
+    // equal tiles in lock-step rounds: the last round of ceil(n_tiles / slots) is only partly filled.  Among 2..per_sm
+    // resident CTAs take the count that wastes the least of it (ties: the larger count).
+    int best = per_sm;
+    double best_eff = 0.0;
+    for (int k = per_sm; k >= 2; --k) {
+      const double x = (double)n_tiles / ((double)k * bn_sm_count());
+      const double eff = x / (double)(long long)(x + 0.999999);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = k; }
+    }
+    per_sm = best;
+  }
   int grid = per_sm * bn_sm_count();
   return grid < n_tiles ? grid : n_tiles;
 }

@@ -30,6 +30,10 @@ namespace dards {
 int g_dbg_lbo = -1, g_dbg_version = -1, g_dbg_sbo = -1, g_dbg_base_offset_mode = -1, g_dbg_epilogue = -1, g_dbg_conv3 = -1, g_dbg_stages = -1, g_dbg_wgrad_fuse = -1, g_dbg_tile_balance = -1;
 int g_dbg_l2_hint = -1;
 extern int g_dbg_cb_pertap, g_dbg_cb_bstages, g_dbg_cb_wide, g_dbg_cb_share;
+extern int g_dbg_bn_shift, g_dbg_bn_k;  // bn.cu
+extern int g_dbg_wgrad_pair;             // wgrad_tc.cu
+int g_dbg_pair = -1;         // debug key 17 = 0: wide layers stay on the single-CTA kernel instead of tc_conv_pair_kernel
+int g_dbg_pair_stages = -1;  // debug key 18: its operand ring depth (default 6)
 int g_dbg_shared = -1;   // debug key 10: 1 routes the wide (> 128 channel) k3/s1 layers through conv_bn_tc.cu's main loop, 2 all of them
 
 // conv_bn_tc.cu: k3 / s1 / p1 convolution whose weight tiles are shared by two simultaneously accumulated position tiles
@@ -294,6 +298,201 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ===================================================================================================
+// CTA-pair variant of tc_conv_kernel<2> for the wide layers (>= 256 output channels): cta_group::2, M = 256.
+// The per-tap kernel above re-fetches the activation tile for every tap and every output-channel tile, and at
+// C >= 256 its operand stream (44 KB per 4 MMAs = 97 B/clk/SM) runs into the L2 -> SM limit (~12 TB/s, ncu:
+// 478 MB per launch in 40 us) long before the tensor pipe is busy.  Here two CTAs of a cluster take the two
+// output-channel tiles (2j, 2j+1) of the SAME position tile: each loads its own 128 x 64 weight tile and HALF of the
+// activation tile (its nb/2 breaths), and the leader's tcgen05.mma.cta_group::2 reads both halves -- 30 KB per CTA
+// per 4 MMAs instead of 44 KB, and a 32 KB stage leaves room for a 6-deep ring.  Each CTA's TMEM receives the 128
+// accumulator lanes of its own channel tile, so the epilogue (two half-tile TMA stores) is unchanged.
+// Protocol: full[s] lives in the LEADER (its producer expects the bytes of both CTAs; both CTAs' TMA loads signal it);
+// empty[s] and tmem_full[b] live in both CTAs and are signalled by the leader's multicast commits; tmem_empty[b]
+// lives in the leader and collects one arrive per epilogue warp of both CTAs.
+// ===================================================================================================
+constexpr int TP_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES / 2;  // 32 KB
+constexpr int TP_MAX_STAGES = 6;
+static int tp_smem_bytes(int stages) { return stages * TP_STAGE_BYTES + TC_STAGING_BYTES / 2 + 1024 + 256; }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    tc_conv_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                        const __grid_constant__ CUtensorMap tm_o, const TcConvParams p, uint32_t desc_lbo16,
+                        uint32_t desc_sbo16, uint32_t desc_version) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int n_stages = p.stages;
+  const uint32_t staging = smem_base + n_stages * TP_STAGE_BYTES;
+  const uint32_t bar_base = staging + TC_STAGING_BYTES / 2;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (TP_MAX_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * TP_MAX_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * TP_MAX_STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TP_MAX_STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool lead = rank == 0;
+  const int n_tile = p.nb * p.l_tile;
+  const int n_co_pairs = p.n_co_tiles >> 1;
+  const int total_jobs = p.n_pos_tiles * n_co_pairs;
+  const int first_job = (int)(blockIdx.x >> 1), job_step = (int)(gridDim.x >> 1);
+  const int k_steps = p.n_taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_o);
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 2 * TC_EPI_WARPS);  // one arrive per epilogue warp of BOTH CTAs (used in the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer (both CTAs) ===========================
+    const bool issuer = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t stage_tx = TC_A_BYTES + (uint32_t)(n_tile >> 1) * (TC_BLOCK_K * 2);
+    const int nb_half = p.nb >> 1;
+    for (int job = first_job; job < total_jobs; job += job_step) {
+      const int co_tile = 2 * (job % n_co_pairs) + (int)rank, pos_tile = job / n_co_pairs;
+      const int co0 = co_tile * TC_BLOCK_M, n0 = pos_tile * p.nb + (int)rank * nb_half;
+      for (int ti = 0; ti < p.n_taps; ++ti) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait_tight(empty_bar(stage), phase ^ 1u);
+          if (issuer) {
+            const uint32_t sa = smem_base + stage * TP_STAGE_BYTES, sb = sa + TC_A_BYTES;
+            const uint32_t fb = full_bar(stage) & TC_PEER_MASK;  // the leader's barrier
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), 2u * stage_tx);
+            tma_load_3d_2sm(sa, &tm_w, fb, kc * TC_BLOCK_K, co0, p.w_tap[ti]);
+            tma_load_4d_2sm(sb, &tm_x, fb, kc * TC_BLOCK_K, p.in_par[ti], p.in_start[ti], n0);
+          }
+          if (++stage == n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (lead) {
+      const bool issuer = elect_one();
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_tile >> 3) << 17) |
+                             ((uint32_t)((2 * TC_BLOCK_M) >> 4) << 24);
+      const uint64_t tmpl = make_sw128_desc(0, desc_lbo16, desc_sbo16, desc_version, 0);
+      const uint32_t desc_hi = (uint32_t)(tmpl >> 32);
+      // the descriptor's 14-bit address field holds the CTA-relative address: drop the cluster-rank bits
+      const uint32_t a_lo0 = (uint32_t)tmpl + ((smem_base & 0x3FFFFu) >> 4);
+      const uint32_t step = TP_STAGE_BYTES >> 4;
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      uint32_t a_lo = a_lo0, fb = full_bar(0), eb = empty_bar(0);
+      for (int job = first_job; job < total_jobs; job += job_step, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait_tight(tempty_bar(buf), acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_MAX_N;
+        uint32_t acc = 0u;
+        for (int ks = 0; ks < k_steps; ++ks) {
+          mbar_wait_tight(fb, phase);
+          tc_fence_after();
+          if (issuer) {
+            const uint32_t b_lo = a_lo + (TC_A_BYTES >> 4);
+            umma2_bf16_lo(d_tmem, a_lo, b_lo, desc_hi, idesc, acc);
+            umma2_bf16_lo(d_tmem, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+            umma2_bf16_lo(d_tmem, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+            umma2_bf16_lo(d_tmem, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+            umma2_commit_mc(eb, 3u);  // frees the stage in both CTAs
+          }
+          acc = 1u;
+          a_lo += step; fb += 8; eb += 8;
+          if (++stage == n_stages) {
+            stage = 0; phase ^= 1u; a_lo = a_lo0; fb = full_bar(0); eb = empty_bar(0);
+          }
+        }
+        if (issuer) umma2_commit_mc(tfull_bar(buf), 3u);  // accumulators complete -> both epilogues
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..9 of both CTAs): two half-tile TMA stores ===========
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int cl = quarter * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
+    const int cols_h = n_tile >> 1;
+    __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_gen + (staging - smem_base));
+    int it = 0;
+    for (int job = first_job; job < total_jobs; job += job_step, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int co_tile = 2 * (job % n_co_pairs) + (int)rank, pos_tile = job / n_co_pairs;
+      const int co0 = co_tile * TC_BLOCK_M, n0 = pos_tile * p.nb;
+      mbar_wait(tfull_bar(buf), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * TC_MAX_N;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (leader) tma_store_wait_read();
+        named_bar_sync(1, TC_EPI_THREADS);
+        const int col_lo = h * cols_h, col_hi = col_lo + cols_h;
+        for (int ch = (col_lo >> 4) + half; (ch << 4) < col_hi; ch += 2) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)(ch << 4), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = (ch << 4) + j;
+            if (col >= col_lo && col < col_hi) stg[(col - col_lo) * TC_BLOCK_M + cl] = __float2bfloat16_rn(__uint_as_float(v[j]));
+          }
+        }
+        if (h == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_bar(buf) & TC_PEER_MASK);
+        }
+        fence_proxy_async();
+        named_bar_sync(1, TC_EPI_THREADS);
+        if (leader) {
+          const int nh = n0 + h * (p.nb >> 1);
+          if (p.accumulate) tma_reduce_add_4d(&tm_o, staging, co0, p.out_par, 0, nh);
+          else tma_store_4d(&tm_o, staging, co0, p.out_par, 0, nh);
+          tma_store_commit();
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while its partner may still signal its barriers or read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -652,6 +851,11 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
     p.stages = 4;
     p.halves = 2;
   }
+  // CTA pairs (tc_conv_pair_kernel): long reductions with an even number of full output-channel tiles and a position tile
+  // that splits into two halves of whole 8-row swizzle groups.  Measured (profiles/r02_kbench_conv_pair.txt): 43.9 vs
+  // 48.5 us at C = 512, 27.4 vs 30.6 us at C = 256; debug key 17 = 0 keeps the single-CTA kernel.
+  const bool pair = g_dbg_pair != 0 && p.halves == 2 && (g_dbg_epilogue < 0 || g_dbg_epilogue == 1) && q.c_cols % (2 * TC_BLOCK_M) == 0 && n_tile % 16 == 0 &&
+                    (n_tile / 2) % 8 == 0 && q.c_red % TC_BLOCK_K == 0;
   CUtensorMap tm_w, tm_x, tm_o;
   {
     cuuint64_t dims[3] = {(cuuint64_t)q.c_red, (cuuint64_t)q.c_cols, (cuuint64_t)q.ktaps_total};
@@ -665,7 +869,7 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)q.c_red, (cuuint64_t)planes, (cuuint64_t)l_plane, (cuuint64_t)q.n_breaths};
     cuuint64_t str[3] = {(cuuint64_t)q.src_stride * 2, (cuuint64_t)q.src_stride * planes * 2,
                          (cuuint64_t)q.src_stride * q.l_src * 2};
-    cuuint32_t box[4] = {TC_BLOCK_K, 1, (cuuint32_t)p.l_tile, (cuuint32_t)p.nb};
+    cuuint32_t box[4] = {TC_BLOCK_K, 1, (cuuint32_t)p.l_tile, (cuuint32_t)(pair ? p.nb / 2 : p.nb)};
     int rc = make_bf16_map(&tm_x, q.src, 4, dims, str, box, true);
     if (rc) return rc;
   }
@@ -704,6 +908,41 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
   const uint32_t lbo = g_dbg_lbo >= 0 ? (uint32_t)g_dbg_lbo : 1u;
   const uint32_t sbo = g_dbg_sbo >= 0 ? (uint32_t)g_dbg_sbo : (1024u >> 4);
   const uint32_t ver = g_dbg_version >= 0 ? (uint32_t)g_dbg_version : 1u;
+  if (pair) {
+    p.stages = g_dbg_pair_stages > 0 && g_dbg_pair_stages <= TP_MAX_STAGES ? g_dbg_pair_stages : TP_MAX_STAGES;
+    const int pair_smem = tp_smem_bytes(p.stages);
+    static int pair_attr = 0;
+    static int pair_clusters = 0;
+    if (pair_smem > pair_attr) {
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem);
+      if (e != cudaSuccess) {
+        set_error("tcgen05 conv (CTA pairs): cannot opt in to %d bytes of shared memory: %s", pair_smem, cudaGetErrorString(e));
+        return DARDS_ERR_CUDA;
+      }
+      pair_attr = pair_smem;
+      // clusters of 2 that can be resident at once (a GPC with an odd number of usable SMs leaves one out)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * 74);
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = pair_smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, tc_conv_pair_kernel, &cfg) != cudaSuccess || nc <= 0) {
+        cudaGetLastError();
+        nc = sm_count() / 2;
+      }
+      pair_clusters = nc;
+    }
+    int clusters = pair_clusters < sm_count() / 2 ? pair_clusters : sm_count() / 2;
+    if (clusters > tiles / 2) clusters = tiles / 2;
+    tc_conv_pair_kernel<<<2 * clusters, TC_THREADS, pair_smem, st>>>(tm_w, tm_x, tm_o, p, lbo, sbo, ver);
+    DARDS_CHECK_LAUNCH("tc_conv_pair");
+    return DARDS_OK;
+  }
   if (p.halves == 1)
     tc_conv_kernel<1><<<grid, TC_THREADS, smem_bytes, st>>>(tm_w, tm_x, tm_o, static_cast<__nv_bfloat16*>(q.dst), p, lbo, sbo,
                                                             ver);
@@ -888,6 +1127,11 @@ int tc_debug_set(int key, int value) {
   else if (key == 12) g_dbg_cb_bstages = value;
   else if (key == 13) g_dbg_cb_wide = value;
   else if (key == 14) g_dbg_cb_share = value;
+  else if (key == 15) g_dbg_bn_shift = value;
+  else if (key == 16) g_dbg_bn_k = value;
+  else if (key == 17) g_dbg_pair = value;
+  else if (key == 18) g_dbg_pair_stages = value;
+  else if (key == 19) g_dbg_wgrad_pair = value;
   else {
     set_error("tc_debug_set: unknown key %d", key);
     return DARDS_ERR_INVALID_ARGUMENT;

@@ -29,6 +29,8 @@
 
 namespace dards {
 
+int g_dbg_wgrad_pair = -1;  // debug key 19 = 1: C >= 256 layers on CTA pairs (cta_group::2)
+
 constexpr int WG_TC_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int WG_RMAX = 128;             // reduction rows per stage (multiple of 16)
 constexpr int WG_CHUNK_A = WG_RMAX * 128;          // bytes of one 64-channel chunk of the dout tile
@@ -58,9 +60,16 @@ struct WgTcParams {
   int fuse_taps;               // 1: the 3 taps are the 3 column chunks of one N = 192 MMA (c_in == 64, stride 1)
   int tap_cols;                // TMEM column distance between the taps' accumulators (128, or 64 when fused)
   int l2_hint;                 // 1: the saved input activations (their last use) are loaded with L2 evict_first priority
+  int pair;                    // 1: CTA pairs (cta_group::2): two output-channel tiles share one input tile, half of it per CTA
   int accumulate_l2;           // 1: the CTA's tile is ADDED into dw_t[t][co][ci] with TMA reduce-add (no partials, no reduce kernel)
 };
 
+// PAIR: launched as clusters of 2 CTAs along blockIdx.x.  The pair takes the output-channel tiles (2j, 2j+1) of one
+// input-channel tile and one split: M = 256 through tcgen05.mma.cta_group::2, each CTA stages its own dout tile and ONE of
+// the two 64-channel chunks of the input tile (the B operand's N = 128 columns are split between the two CTAs), which cuts
+// the operand stream from 66 to 49 KB per stage -- the single-CTA kernel needs 42 B/clk/SM, exactly the L2 -> SM limit.
+// Barriers as in tc_conv_pair_kernel: full[] in the leader, empty[] / done in both (multicast commits).
+template <bool PAIR>
 __global__ void __launch_bounds__(WG_TC_THREADS, 1)
     tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const __grid_constant__ CUtensorMap tm_d, float* __restrict__ partial, const WgTcParams p) {
@@ -76,9 +85,13 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y;
-  const int co0 = (tile / p.n_ci_tiles) * 128, ci0 = (tile % p.n_ci_tiles) * 128;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool lead = rank == 0;
+  // pairs: (tile >> 1) enumerates (output-channel tile pair, input-channel tile), the rank picks the channel tile
+  const int co0 = PAIR ? (2 * ((tile >> 1) / p.n_ci_tiles) + (int)rank) * 128 : (tile / p.n_ci_tiles) * 128;
+  const int ci0 = PAIR ? ((tile >> 1) % p.n_ci_tiles) * 128 : (tile % p.n_ci_tiles) * 128;
   const int ci_n = (p.c_in - ci0) >= 128 ? 128 : ((p.c_in - ci0 + 63) / 64) * 64;  // MMA N: 64 or 128
-  const int co_chunks = (p.c_out - co0) > 64 ? 2 : 1, ci_chunks = ci_n / 64;
+  const int co_chunks = (p.c_out - co0) > 64 ? 2 : 1, ci_chunks = PAIR ? 1 : ci_n / 64;  // chunks THIS CTA stages
   const int u_begin = split * p.units_per_split;
   int u_end = u_begin + p.units_per_split;
   if (u_end > p.n_units) u_end = p.n_units;
@@ -103,11 +116,17 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_slot, 512);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers exist and both operand areas are cleared
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int rows = p.nb * p.p_rows;  // rows written by TMA per chunk
@@ -125,12 +144,21 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
         mbar_wait_tight(empty_bar(stage), phase ^ 1u);
         if (issuer) {
           const uint32_t sa = smem_base + stage * p.stage_bytes;
-          mbar_arrive_expect_tx(full_bar(stage), tx);
-          for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * WG_CHUNK_A, &tm_a, full_bar(stage), co0 + c * 64, 0, p.a_start, n0);
-          for (int b = 0; b < p.n_btiles; ++b) {
-            const uint32_t sb = sa + p.a_bytes + b * p.b_bytes;
-            for (int c = 0; c < ci_chunks; ++c)
-              tma_load_4d_pol(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0, pol_b);
+          if (PAIR) {
+            const uint32_t fb = full_bar(stage) & TC_PEER_MASK;  // the leader's barrier collects both CTAs' bytes
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), 2u * tx);
+            for (int c = 0; c < co_chunks; ++c) tma_load_4d_2sm(sa + c * WG_CHUNK_A, &tm_a, fb, co0 + c * 64, 0, p.a_start, n0);
+            for (int b = 0; b < p.n_btiles; ++b)
+              tma_load_4d_2sm_pol(sa + p.a_bytes + b * p.b_bytes, &tm_b, fb, ci0 + (int)rank * 64, p.b_plane[b], p.b_start[b], n0,
+                                  pol_b);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), tx);
+            for (int c = 0; c < co_chunks; ++c) tma_load_4d(sa + c * WG_CHUNK_A, &tm_a, full_bar(stage), co0 + c * 64, 0, p.a_start, n0);
+            for (int b = 0; b < p.n_btiles; ++b) {
+              const uint32_t sb = sa + p.a_bytes + b * p.b_bytes;
+              for (int c = 0; c < ci_chunks; ++c)
+                tma_load_4d_pol(sb + c * WG_CHUNK_B, &tm_b, full_bar(stage), ci0 + c * 64, p.b_plane[b], p.b_start[b], n0, pol_b);
+            }
           }
         }
         if (++stage == p.stages) {
@@ -141,11 +169,11 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
     }
   } else if (warp == 1) {
     // MMA issuer: whole warp, one elected lane issues; all descriptor arithmetic on the 32-bit low words
-    {
+    if (!PAIR || lead) {
       const bool issuer = elect_one();
-      // instruction descriptor: D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = ci_n, M = 128
+      // instruction descriptor: D=f32, A=B=bf16, A and B MN-major (bits 15, 16), N = ci_n, M = 128 (256 over a CTA pair)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(ci_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                             ((uint32_t)(ci_n >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       const int k_steps = p.r_pad / 16;
@@ -169,7 +197,9 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
       const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), bf_hi = (uint32_t)(bf_tmpl >> 32);
       const uint32_t b_hi0 = (uint32_t)(b_tmpl[0] >> 32), b_hi1 = (uint32_t)(b_tmpl[1] >> 32), b_hi2 = (uint32_t)(b_tmpl[2] >> 32);
       const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
-      uint32_t s16 = smem_base >> 4, fb = full_bar(0), eb = empty_bar(0);
+      // the descriptors' 14-bit address field is CTA-relative: drop the cluster-rank bits of the shared-window address
+      const uint32_t s16_0 = (smem_base & 0x3FFFFu) >> 4;
+      uint32_t s16 = s16_0, fb = full_bar(0), eb = empty_bar(0);
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait_tight(fb, phase);
         tc_fence_after();
@@ -184,6 +214,24 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
               umma_bf16_lo2(d_tmem[0], a_lo, a_hi, bf, bf_hi, idesc_f, acc);
               a_lo += 128; bf += 128;
               acc = 1u;
+            }
+          } else if (PAIR) {
+            if (n_taps == 3) {
+#pragma unroll 4
+              for (int kk = 0; kk < k_steps; ++kk) {
+                umma2_bf16_lo2(d_tmem[0], a_lo, a_hi, b0, b_hi0, idesc, acc);
+                umma2_bf16_lo2(d_tmem[1], a_lo, a_hi, b1, b_hi1, idesc, acc);
+                umma2_bf16_lo2(d_tmem[2], a_lo, a_hi, b2, b_hi2, idesc, acc);
+                a_lo += 128; b0 += 128; b1 += 128; b2 += 128;
+                acc = 1u;
+              }
+            } else {
+#pragma unroll 4
+              for (int kk = 0; kk < k_steps; ++kk) {
+                umma2_bf16_lo2(d_tmem[0], a_lo, a_hi, b0, b_hi0, idesc, acc);
+                a_lo += 128; b0 += 128;
+                acc = 1u;
+              }
             }
           } else if (n_taps == 3) {
 #pragma unroll 4
@@ -202,14 +250,18 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
               acc = 1u;
             }
           }
-          umma_commit(eb);
+          if (PAIR) umma2_commit_mc(eb, 3u);
+          else umma_commit(eb);
         }
         s16 += stage16; fb += 8; eb += 8;
         if (++stage == p.stages) {
-          stage = 0; phase ^= 1u; s16 = smem_base >> 4; fb = full_bar(0); eb = empty_bar(0);
+          stage = 0; phase ^= 1u; s16 = s16_0; fb = full_bar(0); eb = empty_bar(0);
         }
       }
-      if (issuer) umma_commit(done_bar);
+      if (issuer) {
+        if (PAIR) umma2_commit_mc(done_bar, 3u);
+        else umma_commit(done_bar);
+      }
     }
   } else if (p.accumulate_l2) {
     // epilogue, accumulate mode: the fp32 tile of every tap goes through shared memory (the operand ring is idle once the
@@ -282,9 +334,11 @@ __global__ void __launch_bounds__(WG_TC_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the partner may still signal this CTA's barriers / read its operands until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -377,8 +431,10 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   p.n_co_tiles = ceil_div(c_out, 128);
   // a stage holds 1 or 2 64-channel chunks of each operand: narrow layers get a deeper ring out of the same shared
   // memory (they are load-latency bound: the reduction streams activations straight from HBM)
+  p.fuse_taps = (ktaps == 3 && stride == 1 && c_in == 64 && g_dbg_wgrad_fuse != 0) ? 1 : 0;
+  p.pair = (g_dbg_wgrad_pair == 1 && c_out % 256 == 0 && c_in % 128 == 0 && !p.fuse_taps) ? 1 : 0;
   p.a_bytes = (c_out > 64 ? 2 : 1) * WG_CHUNK_A;
-  p.b_bytes = (c_in > 64 ? 2 : 1) * WG_CHUNK_B;
+  p.b_bytes = (c_in > 64 && !p.pair ? 2 : 1) * WG_CHUNK_B;
   p.stage_bytes = p.a_bytes + p.n_btiles * p.b_bytes;
   p.stages = (WG_SMEM_LIMIT - 2048) / p.stage_bytes;
   if (p.stages > WG_MAX_STAGES) p.stages = WG_MAX_STAGES;
@@ -395,7 +451,6 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   // memory address bits, so a descriptor whose start is advanced by whole 128-byte rows needs base_offset = 0;
   // base_offset = (start >> 7) & 7 gives wrong results for the shifted taps.
   p.base_offset_mode = g_dbg_base_offset_mode >= 0 ? g_dbg_base_offset_mode : 1;
-  p.fuse_taps = (ktaps == 3 && stride == 1 && c_in == 64 && g_dbg_wgrad_fuse != 0) ? 1 : 0;
   p.tap_cols = p.fuse_taps ? 64 : 128;
   p.l2_hint = g_dbg_l2_hint != 0 ? 1 : 0;
   w.ok = true;
@@ -458,17 +513,37 @@ static int wg_launch(WgPlan& w, const void* in, const void* dout, float* partial
     if (rc) return rc;
   }
   const int smem = p.stages * p.stage_bytes + 1024 + 256;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int attr_smem[2] = {0, 0};
+  if (smem > attr_smem[p.pair]) {
+    cudaError_t e = p.pair ? cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                           : cudaFuncSetAttribute(tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("tcgen05 wgrad: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
       return DARDS_ERR_CUDA;
     }
-    attr_smem = smem;
+    attr_smem[p.pair] = smem;
   }
   dim3 grid(p.n_ci_tiles * p.n_co_tiles, w.splits);
-  tc_wgrad_kernel<<<grid, WG_TC_THREADS, smem, st>>>(tm_a, tm_b, tm_d, partial, p);
+  if (p.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;                 // grid.x is even (c_out % 256 == 0): clusters of 2 along x share blockIdx.y
+    cfg.blockDim = dim3(WG_TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<true>, tm_a, tm_b, tm_d, partial, p);
+    if (e != cudaSuccess) {
+      set_error("tcgen05 wgrad (CTA pairs): launch failed: %s", cudaGetErrorString(e));
+      return DARDS_ERR_CUDA;
+    }
+    count_launch();
+    return DARDS_OK;
+  }
+  tc_wgrad_kernel<false><<<grid, WG_TC_THREADS, smem, st>>>(tm_a, tm_b, tm_d, partial, p);
   DARDS_CHECK_LAUNCH("tc_wgrad");
   return DARDS_OK;
 }

@@ -315,13 +315,17 @@ class Plan(object):
         l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
         return (self.N, self.group, l_in, l_out, c.cin, c.cout, c.k, c.stride, c.pad)
 
-    def cb_mode(self, c, l_in):
+    def cb_mode(self, c, l_in, merged_branch=False):
         """0: separate conv + BatchNorm kernels; 1: statistics in the convolution epilogue + one elementwise pass;
-        2: BatchNorm (+ residual, + ReLU) entirely in the convolution epilogue."""
+        2: BatchNorm (+ residual, + ReLU) entirely in the convolution epilogue.
+        merged_branch: the layer is one of the two branches of a downsample block, whose two BatchNorms + add + ReLU
+        become ONE elementwise pass in mode 1 (fuse_bn "3" enables mode 1 for those only)."""
         if self.simt_only or self.fuse_bn == "0" or not self._tc_ok(c, "fwd"):
             return 0
         mode = _lib.fn("dards_conv1d_bn_mode")(*self._cb_shape(c, l_in), self.dt)
-        return 0 if (mode == 1 and self.fuse_bn != "1") else mode
+        if mode == 1 and not (self.fuse_bn == "1" or (merged_branch and self.fuse_bn == "3")):
+            return 0
+        return mode
 
     def _cb_conv(self, c, bn, src, src_stride, l_in, y, y_stride, out, out_stride, relu, res, res_stride, st, part,
                  src_last_use):
@@ -333,13 +337,13 @@ class Plan(object):
                      src_stride, y_stride, out_stride, res_stride, c.k, c.stride, c.pad, BN_EPS, flags, self.dt)
 
     def conv_bn_fwd(self, c, bn, src, src_stride, l_in, y, out, relu, res=None, src_last_use=False, ds=None,
-                    part_key="cb_part"):
+                    part_key="cb_part", merged_branch=False):
         """y = conv(src) and out = [relu](bn(y) [+ res] [+ bn_d(conv_d(src_d))]) with the BatchNorm statistics taken in
         the convolution epilogue.  `y` / `out` are (N, l_out, cout) plan buffers, `res` a same-shape buffer;
         ds = (conv record, bn module, source pointer, source stride, source length, y_d buffer): the downsample branch
         of a ResNet block.  Returns (statistics of bn, statistics of the downsample bn or None).  Both convolutions
         must report the same mode (cb_mode)."""
-        mode = self.cb_mode(c, l_in)
+        mode = self.cb_mode(c, l_in, merged_branch)
         l_out = (l_in + 2 * c.pad - c.k) // c.stride + 1
         cout = c.cout
         rows = self.group * l_out
@@ -554,13 +558,13 @@ class Plan(object):
                     st1 = self.gbn_fwd(blk.bn1, y1.data_ptr(), cout, a1.data_ptr(), cout, self.group * lo, cout, True)
                 y2 = self.new((N, lo, cout))
                 out = self.new((N, lo, cout))
-                m2 = self.cb_mode(c2, lo)
+                m2 = self.cb_mode(c2, lo, blk.downsample is not None)
                 if blk.downsample is not None:
                     cd = self.conv(blk.downsample[0])
                     yd = self.new((N, lo, cout))
-                    if m2 and self.cb_mode(cd, L) == m2:
+                    if m2 and self.cb_mode(cd, L, True) == m2:
                         st2, std = self.conv_bn_fwd(c2, blk.bn2, a1.data_ptr(), cout, lo, y2, out, True, src_last_use=True,
-                                                    ds=(cd, blk.downsample[1], a.data_ptr(), cin, L, yd))
+                                                    ds=(cd, blk.downsample[1], a.data_ptr(), cin, L, yd), merged_branch=True)
                     else:
                         self.conv_fwd(c2, a1.data_ptr(), cout, y2.data_ptr(), cout, lo, src_last_use=True)
                         self.conv_fwd(cd, a.data_ptr(), cin, yd.data_ptr(), cout, L)

@@ -167,6 +167,40 @@ def test_conv_tcgen05_wave_balanced_tile_width(case):
         assert rel_err(outs[-1][0].float(), ref) < 6e-3
 
 
+PAIR_CASES = [
+    (23, 256, 512, 14, 3, 2, 1),    # stride 2, ragged: the second CTA's half tile is partly / entirely out of bounds
+    (33, 512, 512, 7, 3, 1, 1),
+    (640, 256, 256, 14, 3, 1, 1),   # 80 pair jobs: several rounds of the 6-stage ring and of the TMEM double buffer
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_tcgen05_cta_pair_kernel_equals_single_cta_kernel(case):
+    """tcgen05.mma.cta_group::2 (two CTAs = two output-channel tiles sharing one activation tile, half of it staged by
+    each) accumulates every output element over the same K order as the single-CTA kernel: forward, dgrad and in-place
+    dgrad (TMA reduce-add) are bit-identical; the weight-gradient kernel's pair mode likewise (deterministic reduce)."""
+    from deepards_b200 import _lib
+    n, cin, cout, l, k, s, p = case
+    x, w, dy = _conv_inputs(case, 5)
+    xb, dyb = cl(x.bfloat16()), cl(dy.bfloat16())
+    add = torch.randn(n, l, cin, device=DEV).bfloat16()
+    outs = {}
+    for mode in (0, 1):
+        _lib.call("dards_tc_debug_set", 17, mode)
+        _lib.call("dards_tc_debug_set", 19, mode)
+        try:
+            outs[mode] = (K().conv1d_fwd(xb, w, s, p, impl=1), K().conv1d_dgrad(dyb, w, l, s, p, impl=1),
+                          K().conv1d_dgrad(dyb, w, l, s, p, impl=1, addend=add), K().conv1d_wgrad(xb, dyb, k, s, p, impl=1))
+        finally:
+            _lib.call("dards_tc_debug_set", 17, -1)
+            _lib.call("dards_tc_debug_set", 19, -1)
+    torch.cuda.synchronize()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    ref = cl(F.conv1d(xb.permute(0, 2, 1).float(), w.bfloat16().float(), stride=s, padding=p))
+    assert rel_err(outs[1][0].float(), ref) < 6e-3
+
+
 def test_conv_tcgen05_direct_store_epilogue_matches_tma_store():
     from deepards_b200 import _lib
     case = CONV_CASES[3]

@@ -1,10 +1,9 @@
 #!/bin/bash
+# ncu --set full of the fused conv+BN kernel alone (C=512 L=7 and C=256 L=14), with source-level stall attribution
 mkdir -p gpurun_out
-T=${1:-r2n}
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_model_parity_gpu.py tests/test_trainer_gpu.py tests/test_extra_gpu.py -m gpu -q -p no:cacheprovider 2>&1 | tail -3
-for F in 0 2 0 2; do
-DEEPARDS_B200_FUSE_BN=$F timeout 600 python bench.py --no-cpu > gpurun_out/${T}_bench_fuse$F.json 2> gpurun_out/${T}_bench_fuse$F.err; echo "resnet FUSE_BN=$F:"; python -c "import json;d=json.load(open('gpurun_out/${T}_bench_fuse$F.json'));print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"
-done
-for F in 0 2; do
-DEEPARDS_B200_FUSE_BN=$F timeout 600 python bench.py --no-cpu --backbone densenet18 > gpurun_out/${T}_bench_dense_fuse$F.json 2> gpurun_out/${T}_bench_dense_fuse$F.err; echo "densenet FUSE_BN=$F:"; python -c "import json;d=json.load(open('gpurun_out/${T}_bench_dense_fuse$F.json'));print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'])"
-done
+export KBENCH_NO_GRAPH=1 KBENCH_SHAPES=${SHAPES:-512x7}
+CMD="python tools/kbench.py convbn"
+$CMD > gpurun_out/n_plain.log 2>&1 || { echo "plain failed"; tail -5 gpurun_out/n_plain.log; exit 1; }
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"tc_conv_bn_kernel" -s 8 -c 2 -f -o gpurun_out/convbn_${TAG:-a} $CMD > gpurun_out/n_ncu.log 2>&1
+tail -3 gpurun_out/n_ncu.log
+ls -la gpurun_out/convbn_${TAG:-a}.ncu-rep

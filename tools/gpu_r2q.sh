@@ -1,15 +1,16 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T=${1:-r2q}
-timeout 1200 python -m pytest tests/test_model_parity_gpu.py -m gpu -q -p no:cacheprovider -s > gpurun_out/${T}_parity.log 2>&1; echo "exit $?"; grep -E "bf16|worst grad|config1|passed|failed|Error" gpurun_out/${T}_parity.log | cut -c1-250 | head -30
-grep -E "worst grad|config1|bf16 B=256|trajectory|bf16:" gpurun_out/${T}_parity.log > gpurun_out/${T}_parity_report.txt
-timeout 600 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench exit $?"; tail -3 gpurun_out/${T}_bench.err
-python - <<PY
+run() {
+  local label=$1; shift
+  env "$@" timeout 300 python bench.py --no-extra --no-cpu --steps 60 --warmup 10 > gpurun_out/q_${label}.json 2> gpurun_out/q_${label}.err || { echo "$label FAILED"; tail -3 gpurun_out/q_${label}.err; return; }
+  python - <<PY
 import json
-d=json.load(open('gpurun_out/${T}_bench.json'))
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')})
-print('e2e',d['e2e']); print('sustained',d.get('sustained')); print('module_path',d.get('module_path'))
-dn=d.get('densenet18'); print('densenet18', {k:dn[k] for k in ('value','ms_per_step','gpu_launches')} if dn else None, dn and dn.get('roofline',{}).get('frac'))
-r=d['roofline']; print('roofline',{k:r[k] for k in ('kernel','bound','achieved','peak','frac','share_of_step')}); print(r['breakdown_ms_per_step'])
-print('cpu', d.get('cpu_baseline'))
+d=json.load(open('gpurun_out/q_${label}.json'))
+bd=d['roofline']['breakdown_ms_per_step']
+print('%-14s %9.0f seq/s  %.4f ms | dgrad %.4f fwd %.4f convbn %.4f wgrad %.4f' % ('${label}', d['value'], d['ms_per_step'], bd.get('dards_conv1d_dgrad:tcgen05',0), bd.get('dards_conv1d_fwd:tcgen05',0), bd.get('dards_conv1d_bn_fwd',0), bd.get('dards_conv1d_wgrad_accum',0)))
 PY
+}
+run base A=1
+run pair DEEPARDS_B200_TC_DEBUG=17=1
+run base2 A=1
+run pair2 DEEPARDS_B200_TC_DEBUG=17=1

@@ -1,17 +1,22 @@
 #!/bin/bash
+# A/B sweep of scheduling knobs on the full step (ResNet-18 and DenseNet-18), one bench line each.
 mkdir -p gpurun_out
-T=${1:-r2x}; N=${2:-2}
-run() { name=$1; shift; env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 40 --warmup 5 --no-cpu --no-extra > gpurun_out/${T}_$name.json 2> gpurun_out/${T}_$name.err; python - <<PY
+run() {  # label, env assignments...
+  local label=$1; shift
+  for bb in resnet18 densenet18; do
+    env "$@" timeout 300 python bench.py --no-extra --no-cpu --backbone $bb --steps 60 --warmup 10 > gpurun_out/x_${label}_${bb}.json 2> gpurun_out/x_${label}_${bb}.err || { echo "$label $bb FAILED"; tail -3 gpurun_out/x_${label}_${bb}.err; continue; }
+    python - <<PY
 import json
-try:
-    d=json.load(open('gpurun_out/${T}_$name.json')); print('$name: %.0f seq/s %.3f ms e2e %.0f' % (d['value'], d['ms_per_step'], d['e2e']['value']))
-except Exception as e:
-    print('$name: no json', e); print(open('gpurun_out/${T}_$name.err').read()[-800:])
+d=json.load(open('gpurun_out/x_${label}_${bb}.json'))
+print('%-28s %-10s %9.0f seq/s  %.4f ms  launches/step %d' % ('${label}', '${bb}', d['value'], d['ms_per_step'], d['gpu_launches']//d['steps']))
 PY
+  done
 }
-run b2M_r8 DEEPARDS_B200_DP_BUCKET_ELEMS=2097152
-run b2M_r0 DEEPARDS_B200_DP_BUCKET_ELEMS=2097152 DEEPARDS_B200_DP_SM_RESERVE=0
-run b2M_r4 DEEPARDS_B200_DP_BUCKET_ELEMS=2097152 DEEPARDS_B200_DP_SM_RESERVE=4 NCCL_MAX_NCHANNELS=4
-run b4M_r0 DEEPARDS_B200_DP_BUCKET_ELEMS=4194304 DEEPARDS_B200_DP_SM_RESERVE=0
-run b4M_r0_ch32 DEEPARDS_B200_DP_BUCKET_ELEMS=4194304 DEEPARDS_B200_DP_SM_RESERVE=0 NCCL_MAX_NCHANNELS=32
-run b1M_r8 DEEPARDS_B200_DP_BUCKET_ELEMS=1048576
+DEEPARDS_B200_TC_DEBUG="15=1,16=1" timeout 600 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider -x -k "gbn or bn" 2>&1 | tail -2
+run base A=1
+run bn_k DEEPARDS_B200_TC_DEBUG=16=1
+run bn_shift_k DEEPARDS_B200_TC_DEBUG=15=1,16=1
+run bn_shift DEEPARDS_B200_TC_DEBUG=15=1
+run tile_balance DEEPARDS_B200_TC_DEBUG=8=1
+run fuse3 DEEPARDS_B200_FUSE_BN=3
+run base2 A=1

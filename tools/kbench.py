@@ -242,6 +242,12 @@ if __name__ == "__main__":
         _lib.call("dards_tc_debug_set", 13, int(os.environ["KBENCH_CB_WIDE"]))
     if os.environ.get("KBENCH_CB_PERTAP"):
         _lib.call("dards_tc_debug_set", 11, int(os.environ["KBENCH_CB_PERTAP"]))
+    if os.environ.get("KBENCH_PAIR"):
+        _lib.call("dards_tc_debug_set", 17, int(os.environ["KBENCH_PAIR"]))   # 1: wide layers on the cta_group::2 kernel
+    if os.environ.get("KBENCH_PAIR_STAGES"):
+        _lib.call("dards_tc_debug_set", 18, int(os.environ["KBENCH_PAIR_STAGES"]))
+    if os.environ.get("KBENCH_WGRAD_PAIR"):
+        _lib.call("dards_tc_debug_set", 19, int(os.environ["KBENCH_WGRAD_PAIR"]))   # 1: C >= 256 weight gradients on CTA pairs
     if os.environ.get("KBENCH_STAGES"):
         _lib.call("dards_tc_debug_set", 6, int(os.environ["KBENCH_STAGES"]))
     for wname in what:
