@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider -x -k "tcgen05" 2>&1 | tail -4
-timeout 300 python bench.py --no-extra --no-cpu --steps 60 --warmup 10 > gpurun_out/p_bench.json 2> gpurun_out/p_bench.err; python -c "
-import json; d=json.load(open('gpurun_out/p_bench.json')); print(d['value'], d['ms_per_step'])"
+DEEPARDS_B200_TC_DEBUG=21=4 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider -x -k "wgrad" 2>&1 | tail -3
+for a in 0 2 4 8; do
+  echo "== wgrad L2 prefetch distance = $a"
+  KBENCH_WGRAD_PREFETCH=$a timeout 200 python tools/kbench.py conv 2>&1 | grep 'wgacc'
+done

@@ -107,7 +107,14 @@ def conv():
             _lib.call("dards_conv1d_wgrad", xs[k].data_ptr(), outs[k].data_ptr(), dw.data_ptr(), 0, ws.data_ptr(),
                       ws.numel() * 4, N, l, l, c, c, c, c, 3, 1, 1, _lib.BF16, 1, st())
 
-        for name, fn in (("fwd", f), ("dgrad", d), ("wgrad", wg)):
+        dwt = torch.zeros(3, c, c, device=DEV)
+
+        def wga(i):  # accumulate mode (what the training step runs): L2 reduce-adds into the tap-major buffer, no reduce kernel
+            k = i % ROT
+            _lib.call("dards_conv1d_wgrad_accum", xs[k].data_ptr(), outs[k].data_ptr(), dwt.data_ptr(), N, l, l, c, c, c, c,
+                      3, 1, 1, _lib.BF16, st())
+
+        for name, fn in (("fwd", f), ("dgrad", d), ("wgrad", wg), ("wgacc", wga)):
             t = timeit(fn)
             print("conv %-5s C=%3d L=%2d k3 s1: %6.1f us  %6.1f TFLOP/s" % (name, c, l, t, fl / t * 1e-6), flush=True)
 

@@ -65,7 +65,10 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int mode, int reps, int p
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
   if (threadIdx.x == 0) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // modes 12..14: MN-major operands (the weight-gradient kernel's layout: rows = K index, 128-byte row = 64 elements of M/N)
+    if (mode == 12 || mode == 13) idesc |= 1u << 15;
+    if (mode == 12 || mode == 14) idesc |= 1u << 16;
     uint32_t phase = 0;
     long long best = 1ll << 60;
     for (int r = 0; r < reps; ++r) {
@@ -80,6 +83,14 @@ __global__ void __launch_bounds__(128, 1) probe(int n, int mode, int reps, int p
           bd[j] = make_desc(sa + a_bytes) + 2 * (j & 3);
           if (mode == 5) bd[j] += 8 * ((j >> 2) % 3);      // taps: B start advanced by 0 / 1 / 2 rows
           if (mode == 8) bd[j] += 8 * 1;                   // every MMA one row off the swizzle atom
+          if (mode >= 12) {
+            // MN-major: a K step of 16 = 16 rows = 2048 bytes; LBO = distance between 64-column chunks (8 KB here)
+            const uint64_t lbo = (uint64_t)(8192 >> 4) << 16;
+            ad[j] = (make_desc(sa) & ~((uint64_t)0x3FFF << 16)) | lbo;
+            bd[j] = (make_desc(sa + a_bytes) & ~((uint64_t)0x3FFF << 16)) | lbo;
+            ad[j] += 128 * (j & 3);
+            bd[j] += 128 * (j & 3);
+          }
         }
         const uint32_t t1 = tmem + (uint32_t)((n + 31) / 32 * 32 > 256 ? 0 : n);  // second accumulator right behind the first
         for (int i = 0; i < per_batch; i += 16) {
@@ -135,9 +146,9 @@ int main() {
   long long* out;
   cudaMalloc(&out, 148 * sizeof(long long));
   const int per_batch = 256;
-  const char* names[12] = {"SS same tile", "SS row-shifted B (taps)", "A from TMEM", "SS k-advance, 4-tile ring", "lean: SS k-advance", "lean: SS taps (B +0/1/2 rows)", "lean: SS two accumulators", "lean: A from TMEM", "lean: SS B +1 row always", "lean: commit every 4 MMAs", "lean: commit every 8 MMAs", "lean: commit every 16 MMAs"};
+  const char* names[15] = {"SS same tile", "SS row-shifted B (taps)", "A from TMEM", "SS k-advance, 4-tile ring", "lean: SS k-advance", "lean: SS taps (B +0/1/2 rows)", "lean: SS two accumulators", "lean: A from TMEM", "lean: SS B +1 row always", "lean: commit every 4 MMAs", "lean: commit every 8 MMAs", "lean: commit every 16 MMAs", "lean: A and B MN-major", "lean: A MN-major", "lean: B MN-major"};
   for (int grid : {148}) {
-    for (int mode : {4, 9, 10, 11}) {
+    for (int mode : {4, 12, 13, 14}) {
       for (int n : {64, 128, 144, 160, 192, 224, 256}) {
         probe<<<grid, 128, smem>>>(n, mode, 5, per_batch, out);
         cudaError_t e = cudaDeviceSynchronize();
