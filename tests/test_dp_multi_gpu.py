@@ -67,9 +67,19 @@ def test_two_rank_step_equals_single_process_step(backbone, use_graph):
     r0, r1 = res
     assert torch.equal(r0["params"], r1["params"])                    # replicas stay identical
     # the global mean loss = sequence-weighted mean of the ranks' local means
-    for l0, l1, lr in zip(r0["losses"], r1["losses"], r0["ref_losses"]):
-        assert abs((l0 * r0["n"] + l1 * r1["n"]) / 5 - lr) <= 1e-4
+    combined = [(l0 * r0["n"] + l1 * r1["n"]) / 5 for l0, l1 in zip(r0["losses"], r1["losses"])]
+    diffs = [abs(lc - lr) for lc, lr in zip(combined, r0["ref_losses"])]
+    # Step 1 runs on identical weights: with dropout on, a wrong mask moves the loss by > 1e-3, identical masks leave
+    # rounding noise.  Later steps compare two fp32 trajectories whose gradients differ in summation order; with the
+    # clamp at 0.01 and lr 1e-2 such trajectories part quickly (tools/dropout_sensitivity.py,
+    # profiles/r02_dropout_sensitivity.txt: a 1e-7 perturbation of the initial weights grows to 1e-3 in the loss within
+    # these 5 steps, with or without dropout), so the dropout case -- measured 2.4e-4 at step 5 -- gets a wider band; the
+    # masks themselves are held bit for bit by tests/test_model_parity_gpu.py::test_dropout_*_ragged_split_*.
+    assert diffs[0] <= 1e-6, diffs
+    tol = 5e-4 if "dropout" in backbone else 1e-4
+    assert max(diffs) <= tol, (diffs, combined, r0["ref_losses"])
     ref = r0["ref_params"]
     err = float((r0["params"] - ref).abs().max() / ref.abs().max())
-    assert err <= 1e-4, err
-    print("%s graph=%s: 2-rank vs single-process parameters after 5 steps: rel err %.2e" % (backbone, use_graph, err))
+    assert err <= tol, err
+    print("%s graph=%s: 2-rank vs single-process: loss |diff| per step %s, parameters after 5 steps rel err %.2e" %
+          (backbone, use_graph, " ".join("%.1e" % d for d in diffs), err))

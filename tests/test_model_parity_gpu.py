@@ -417,3 +417,76 @@ def test_dropout_masks_do_not_depend_on_the_sharding():
     assert torch.equal(run(x[2:], 2), whole[2:])
     assert torch.equal(run(x[:2], 0), whole[:2])
     assert not torch.equal(run(x[2:], 0), whole[2:])      # without the offset the shard would reuse the masks of [0, 2)
+
+
+def test_dropout_masks_of_a_ragged_split_over_several_steps():
+    """The 3 + 2 split of tests/test_dp_multi_gpu.py, forward only, fp32, five consecutive steps of the same plans (the
+    step counter is part of the Philox key): each shard's logits equal its rows of the whole batch bit for bit at every
+    step, and the masks change from step to step."""
+    import deepards_b200 as D
+    from deepards_b200 import engine
+    from deepards_b200.torch_cnn_linear_network import _drop_key
+    sd = O.cnn_linear_state("densenet18", seed=41, bn_perturb=0.1)
+    x = O.synthetic_breaths(5, seed=500).cuda()
+
+    def plan_for(n_seq, first):
+        net = D.CNNLinearNetwork(D.densenet18(drop_rate=0.2), 20, 0)
+        net.load_state_dict(sd)
+        net = net.cuda().train()
+        net.precision = "fp32"
+        plan = engine.get_plan(net, net.breath_block, net.linear_final, n_seq * 20, 20, "fp32", "cnn_linear",
+                               dropout=_drop_key(net.breath_block), update_running=True)
+        assert plan.dropout
+        plan.set_sequence_offset(first)
+        return net, plan
+
+    (n_w, whole), (n_a, a), (n_b, b) = plan_for(5, 0), plan_for(3, 0), plan_for(2, 3)
+    prev = None
+    for step in range(5):
+        outs = []
+        for plan, xs in ((whole, x), (a, x[:3]), (b, x[3:])):
+            plan.load_input(xs)
+            plan.run_forward()
+            plan.mark_no_backward()
+            torch.cuda.synchronize()
+            outs.append(plan.logits.clone())
+        assert torch.equal(outs[1], outs[0][:3]) and torch.equal(outs[2], outs[0][3:]), step
+        assert prev is None or not torch.equal(prev, outs[0])
+        prev = outs[0]
+
+
+def test_dropout_backward_masks_of_a_ragged_split_add_up():
+    """Backward of the same 3 + 2 split: with the loss sum(w * logits), the parameter gradient of the whole batch is the
+    sum of the two shards' gradients (each shard regenerates its masks from the global sequence index in the backward
+    pass too) -- three consecutive steps, fp32."""
+    import deepards_b200 as D
+    from deepards_b200 import engine
+    from deepards_b200.torch_cnn_linear_network import _drop_key
+    sd = O.cnn_linear_state("densenet18", seed=41, bn_perturb=0.1)
+    x = O.synthetic_breaths(5, seed=501).cuda()
+    w = torch.randn(5, 2, device="cuda")
+    keep = []
+
+    def plan_for(n_seq, first):
+        net = D.CNNLinearNetwork(D.densenet18(drop_rate=0.2), 20, 0)
+        net.load_state_dict(sd)
+        net = net.cuda().train()
+        net.precision = "fp32"
+        keep.append(net)
+        plan = engine.get_plan(net, net.breath_block, net.linear_final, n_seq * 20, 20, "fp32", "cnn_linear",
+                               dropout=_drop_key(net.breath_block), update_running=True)
+        plan.set_sequence_offset(first)
+        return plan
+
+    plans = [(plan_for(5, 0), x, w), (plan_for(3, 0), x[:3], w[:3]), (plan_for(2, 3), x[3:], w[3:])]
+    for step in range(3):
+        grads = []
+        for plan, xs, ws in plans:
+            plan.load_input(xs)
+            plan.run_forward()
+            plan.dlogits.copy_(ws.reshape(plan.dlogits.shape))
+            plan.run_backward()
+            torch.cuda.synchronize()
+            grads.append(plan.grad_flat.clone())
+        err = float((grads[1] + grads[2] - grads[0]).abs().max() / grads[0].abs().max())
+        assert err <= 1e-5, (step, err)
