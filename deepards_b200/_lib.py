@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdeepards_b200.so")
 
 F32, BF16 = 0, 1
 HINT_LAST_USE = 0x100   # DARDS_HINT_LAST_USE: OR-ed into `impl` (conv fwd / dgrad) or `relu` (gbn_fwd)
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 P, I, LL, ULL, F, D = c_void_p, c_int, c_longlong, c_ulonglong, c_float, c_double
 
@@ -50,8 +50,9 @@ _SIGNATURES = {
     "dards_reduce_rows_batched": [P, I, I, P],
     "dards_bn_running_update_batched": [P, I, I, F, P],
     "dards_bn_running_update": [P, P, P, P, P, I, I, I, F, F, P],
-    "dards_stem_fwd": [P, P, P, P, P, P, P, I, I, I, I, F, I, I, P],
-    "dards_stem_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "dards_stem_workspace_bytes": [I, I, I, I],
+    "dards_stem_fwd": [P, P, P, P, P, P, P, I, I, I, I, F, I, P, LL, I, P],
+    "dards_stem_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, P, LL, I, P],
     "dards_avgpool2_fwd": [P, P, I, I, I, I, I, I, P],
     "dards_avgpool2_bwd": [P, P, I, I, I, I, I, I, P],
     "dards_avgpool_full_fwd": [P, P, I, I, I, I, I, P],
@@ -67,7 +68,8 @@ _SIGNATURES = {
     "dards_tc_debug_set": [I, I],
     "dards_set_sm_limit": [I],
 }
-_RESTYPES = {"dards_last_error": ctypes.c_char_p, "dards_launch_count": c_longlong, "dards_conv1d_wgrad_workspace_bytes": c_longlong}
+_RESTYPES = {"dards_last_error": ctypes.c_char_p, "dards_launch_count": c_longlong, "dards_conv1d_wgrad_workspace_bytes": c_longlong,
+             "dards_stem_workspace_bytes": c_longlong}
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
 

@@ -64,9 +64,10 @@ int launch_reduce_rows(const float*, float*, int, int, int, cudaStream_t);
 int launch_bn_running_update(const float*, const float*, float*, float*, long long*, int, int, int, float, float,
                              cudaStream_t);
 int launch_stem_fwd(const float*, const float*, const float*, const float*, void*, float*, float*, int, int, int, int,
-                    float, int, int, cudaStream_t);
+                    float, int, void*, long long, int, cudaStream_t);
 int launch_stem_bwd(const void*, const float*, const float*, const float*, const float*, const float*, const float*,
-                    float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
+                    float*, float*, float*, int, int, int, int, int, void*, long long, int, cudaStream_t);
+long long stem_workspace_bytes(int n_groups, int group, int c0, int backward);
 int launch_avgpool2(int, const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int launch_avgpool_full_fwd(const void*, float*, int, int, int, int, int, cudaStream_t);
 int launch_avgpool_full_bwd(const float*, void*, int, int, int, int, int, cudaStream_t);
@@ -92,7 +93,7 @@ using namespace dards;
 
 extern "C" {
 
-int dards_version(void) { return 7; }
+int dards_version(void) { return 8; }
 
 const char* dards_last_error(void) { return g_err; }
 
@@ -314,25 +315,29 @@ int dards_bn_running_update(const float* save_mean, const float* save_rstd, floa
                                   rows_per_group, c, momentum, eps, S(stream));
 }
 
+long long dards_stem_workspace_bytes(int n_groups, int group, int c0, int backward) {
+  return stem_workspace_bytes(n_groups, group, c0, backward ? 1 : 0);
+}
+
 int dards_stem_fwd(const float* x, const float* w, const float* gamma, const float* beta, void* out, float* save_mean,
-                   float* save_rstd, int n_groups, int group, int c0, int out_stride, float eps, int pool, int dtype,
-                   void* stream) {
+                   float* save_rstd, int n_groups, int group, int c0, int out_stride, float eps, int pool, void* workspace,
+                   long long workspace_bytes, int dtype, void* stream) {
   DARDS_CHECK_ARG(x && w && gamma && beta && out && save_mean && save_rstd, "stem_fwd: null pointer");
   DARDS_CHECK_ARG(pool == 0 || pool == 1, "stem_fwd: pool must be 0 (max) or 1 (avg)");
   DARDS_CHECK_ARG(out_stride >= c0, "stem_fwd: row stride smaller than channel count");
-  return launch_stem_fwd(x, w, gamma, beta, out, save_mean, save_rstd, n_groups, group, c0, out_stride, eps, pool, dtype,
-                         S(stream));
+  return launch_stem_fwd(x, w, gamma, beta, out, save_mean, save_rstd, n_groups, group, c0, out_stride, eps, pool, workspace,
+                         workspace_bytes, dtype, S(stream));
 }
 
 int dards_stem_bwd(const void* dout, const float* x, const float* w, const float* gamma, const float* beta,
                    const float* save_mean, const float* save_rstd, float* dw_part, float* dgamma_part,
-                   float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, int dtype,
-                   void* stream) {
+                   float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, void* workspace,
+                   long long workspace_bytes, int dtype, void* stream) {
   DARDS_CHECK_ARG(dout && x && w && gamma && beta && save_mean && save_rstd && dw_part && dgamma_part && dbeta_part,
                   "stem_bwd: null pointer");
   DARDS_CHECK_ARG(pool == 0 || pool == 1, "stem_bwd: pool must be 0 (max) or 1 (avg)");
   return launch_stem_bwd(dout, x, w, gamma, beta, save_mean, save_rstd, dw_part, dgamma_part, dbeta_part, n_groups, group,
-                         c0, dout_stride, pool, dtype, S(stream));
+                         c0, dout_stride, pool, workspace, workspace_bytes, dtype, S(stream));
 }
 
 int dards_avgpool2_fwd(const void* in, void* out, int n_breaths, int l_in, int c, int in_stride, int out_stride,

@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 BN_EPS = 1e-5
-STEM_MAX_GROUP = 226   # stem.cu: forward 236, backward 226 breaths of 224 samples in shared memory
+STEM_FUSED_GROUP = 226   # stem.cu: larger BatchNorm groups run through the chunked stem (two passes, a workspace)
 BN_MOMENTUM = 0.1
 SEQ_LEN = 224
 
@@ -468,20 +468,22 @@ class Plan(object):
         c0 = conv.out_channels
         if conv.in_channels != 1 or conv.kernel_size[0] != 7 or conv.stride[0] != 2 or conv.padding[0] != 3:
             raise NotImplementedError("stem must be Conv1d(1, C0, 7, stride 2, padding 3)")
-        if self.group > STEM_MAX_GROUP:
-            # The fused stem keeps a BatchNorm group's input in shared memory (stem.cu).  Heads that call the backbone per
-            # sequence (group = 20) are far below the limit; a FLAT batch (ResNet.forward(x) / DenseNet.forward(x) /
-            # CNNRegressor: the whole batch is one BatchNorm group) is limited to this many breaths per call.
-            raise NotImplementedError(
-                "deepards_b200: a BatchNorm group of %d breaths exceeds the fused stem's limit of %d (its group input "
-                "lives in shared memory).  Call the backbone on at most %d breaths at a time, or through a sequence head "
-                "(group = sequence length)." % (self.group, STEM_MAX_GROUP, STEM_MAX_GROUP))
         mean, rstd = self.stats(c0)
+        # a BatchNorm group that does not fit the fused stem's shared memory (a flat batch of more than 226 breaths is ONE
+        # group) runs in chunks and needs a workspace for the chunk records (stem.cu)
+        ws, ws_bytes = self._stem_ws(c0, 0)
         self.fwd.add("dards_stem_fwd", self.x_buf.data_ptr(), conv.weight.data_ptr(), bn.weight.data_ptr(),
                      bn.bias.data_ptr(), out, mean.data_ptr(), rstd.data_ptr(), self.G, self.group, c0, out_stride,
-                     BN_EPS, pool, self.dt)
+                     BN_EPS, pool, ws, ws_bytes, self.dt)
         self._note_running(bn, mean, rstd, self.group * 112, c0)
         return mean, rstd
+
+    def _stem_ws(self, c0, backward):
+        nbytes = _lib.fn("dards_stem_workspace_bytes")(self.G, self.group, c0, backward)
+        if not nbytes:
+            return None, 0
+        t = self.new(((nbytes + 3) // 4,), torch.float32)
+        return t.data_ptr(), t.numel() * 4
 
     def _stem_bwd(self, conv, bn, pool, st, dout, dout_stride):
         c0 = conv.out_channels
@@ -489,9 +491,10 @@ class Plan(object):
         dwp = self.new((self.G, c0 * 7), torch.float32)
         dgp = self.new((self.G, c0), torch.float32)
         dbp = self.new((self.G, c0), torch.float32)
+        ws, ws_bytes = self._stem_ws(c0, 1)
         self.bwd.add("dards_stem_bwd", dout, self.x_buf.data_ptr(), conv.weight.data_ptr(), bn.weight.data_ptr(),
                      bn.bias.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(),
-                     self.G, self.group, c0, dout_stride, pool, self.dt)
+                     self.G, self.group, c0, dout_stride, pool, ws, ws_bytes, self.dt)
         self._pending_red.append((dwp, self.G, c0 * 7, self.gptr(conv.weight)))
         self._pending_red.append((dgp, self.G, c0, self.gptr(bn.weight)))
         self._pending_red.append((dbp, self.G, c0, self.gptr(bn.bias)))

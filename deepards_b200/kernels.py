@@ -195,9 +195,17 @@ def stem_fwd(x, w, gamma, beta, group, pool, dtype, eps=1e-5):
     out = torch.empty((n, 56, c0), dtype=dtype, device=x.device)
     mean = torch.empty((g, c0), dtype=torch.float32, device=x.device)
     rstd = torch.empty((g, c0), dtype=torch.float32, device=x.device)
+    ws = _stem_workspace(g, group, c0, 0, x.device)
     _lib.call("dards_stem_fwd", x.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-              mean.data_ptr(), rstd.data_ptr(), g, group, c0, c0, eps, pool, _DT[dtype], _st(x))
+              mean.data_ptr(), rstd.data_ptr(), g, group, c0, c0, eps, pool, ws.data_ptr() if ws is not None else None,
+              ws.numel() * 4 if ws is not None else 0, _DT[dtype], _st(x))
     return out, mean, rstd
+
+
+def _stem_workspace(n_groups, group, c0, backward, device):
+    """Chunk records of the stem's large-group path (None when the group fits the one-kernel path)."""
+    nbytes = _lib.fn("dards_stem_workspace_bytes")(n_groups, group, c0, backward)
+    return torch.empty(((nbytes + 3) // 4,), dtype=torch.float32, device=device) if nbytes else None
 
 
 def stem_bwd(dout, x, w, gamma, beta, mean, rstd, group, pool):
@@ -208,9 +216,11 @@ def stem_bwd(dout, x, w, gamma, beta, mean, rstd, group, pool):
     dwp = torch.empty((g, c0 * 7), dtype=torch.float32, device=dev)
     dgp = torch.empty((g, c0), dtype=torch.float32, device=dev)
     dbp = torch.empty((g, c0), dtype=torch.float32, device=dev)
+    ws = _stem_workspace(g, group, c0, 1, dev)
     _lib.call("dards_stem_bwd", dout.data_ptr(), x.data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
               mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(), g, group, c0,
-              _rowstride(dout), pool, _dt(dout), _st(x))
+              _rowstride(dout), pool, ws.data_ptr() if ws is not None else None, ws.numel() * 4 if ws is not None else 0,
+              _dt(dout), _st(x))
     return dwp.sum(0).view(c0, 1, 7), dgp.sum(0), dbp.sum(0)
 
 

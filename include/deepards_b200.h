@@ -209,15 +209,20 @@ int dards_bn_running_update_batched(const dards_running_desc* descs_dev, int n_d
 
 /* ---- stem: Conv1d(1->C0,k7,s2,p3) + BN + ReLU + Max/AvgPool1d(3,2,1) ---------------- */
 /* resnet.py:143-153 / densenet.py:119-123 fused: x (N,224) fp32 -> out (N,56,C0).  Nothing but the
- * group statistics is saved; the backward recomputes the convolution from x. pool: 0 max, 1 avg. */
+ * group statistics is saved; the backward recomputes the convolution from x. pool: 0 max, 1 avg.
+ * A BatchNorm group of up to 226 breaths (the sequence heads use 20) is one kernel and needs no workspace.  Larger groups
+ * -- a flat batch through ResNet.forward / DenseNet.forward / CNNRegressor is ONE group (resnet.py:141-163) -- run in
+ * chunks of 64 breaths through two passes and need `workspace` of dards_stem_workspace_bytes(...) bytes (0 otherwise;
+ * the pointer may then be NULL). */
+long long dards_stem_workspace_bytes(int n_groups, int group, int c0, int backward);
 int dards_stem_fwd(const float* x, const float* w, const float* gamma, const float* beta, void* out,
                    float* save_mean, float* save_rstd, int n_groups, int group, int c0, int out_stride,
-                   float eps, int pool, int dtype, void* stream);
+                   float eps, int pool, void* workspace, long long workspace_bytes, int dtype, void* stream);
 /* dout (N,56,C0) -> per-group partials dw_part [n_groups][C0][7], dgamma_part/dbeta_part [n_groups][C0]. */
 int dards_stem_bwd(const void* dout, const float* x, const float* w, const float* gamma, const float* beta,
                    const float* save_mean, const float* save_rstd, float* dw_part, float* dgamma_part,
-                   float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, int dtype,
-                   void* stream);
+                   float* dbeta_part, int n_groups, int group, int c0, int dout_stride, int pool, void* workspace,
+                   long long workspace_bytes, int dtype, void* stream);
 
 /* ---- pooling, dropout --------------------------------------------------------------- */
 /* nn.AvgPool1d(2,2) (densenet.py:77): (N,L,C) -> (N,L/2,C) and its backward. */

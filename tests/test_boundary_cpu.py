@@ -25,7 +25,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "library does not export %s" % name
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes binding and header disagree"
-    assert lib.dards_version() == _lib.ABI_VERSION == 7
+    assert lib.dards_version() == _lib.ABI_VERSION == 8
     # the shared object is self-contained: it must not need libcuda / libcudart at load time
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out and "libcudart" not in out
@@ -41,7 +41,11 @@ def test_argument_validation_returns_error_codes_not_crashes():
     rc = lib.dards_linear_fwd(16, 16, 16, 16, 1, 128, 99, None)
     assert rc == -1
     with pytest.raises(RuntimeError, match="deepards_b200"):
-        _lib.call("dards_stem_fwd", 16, 16, 16, 16, 16, 16, 16, 1, 20, 40, 40, 1e-5, 0, 0, None)  # C0 = 40 unsupported
+        _lib.call("dards_stem_fwd", 16, 16, 16, 16, 16, 16, 16, 1, 20, 40, 40, 1e-5, 0, None, 0, 0, None)  # C0 = 40 unsupported
+    # a BatchNorm group beyond the one-kernel stem needs a workspace: asked for, and refused without one
+    assert lib.dards_stem_workspace_bytes(2, 226, 64, 0) == 0 and lib.dards_stem_workspace_bytes(2, 300, 64, 0) == 2 * 5 * 3 * 64 * 4
+    with pytest.raises(RuntimeError, match="needs .* bytes of workspace"):
+        _lib.call("dards_stem_fwd", 16, 16, 16, 16, 16, 16, 16, 2, 300, 64, 64, 1e-5, 0, None, 0, 0, None)
 
 
 @pytest.mark.parametrize("backbone", ["resnet18", "densenet18"])

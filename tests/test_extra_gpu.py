@@ -288,13 +288,40 @@ def test_patient_votes_on_device_match_the_references_loop():
     assert np.array_equal(got, ref)
 
 
-def test_flat_batch_group_limit_is_a_clear_error():
-    """ResNet.forward(x) on a flat batch makes the whole batch one BatchNorm group; beyond 226 breaths the fused
-    stem cannot hold the group in shared memory -- that must be a clear error at plan build, not a kernel failure."""
+def test_flat_batch_of_any_size_is_one_batchnorm_group():
+    """ResNet.forward(x) / DenseNet.forward(x) on a flat batch make the whole batch ONE BatchNorm group
+    (resnet.py:141-163, densenet.py:117-128).  Up to 226 breaths the fused stem holds the group in shared memory; larger
+    groups run through the chunked stem and the streaming BatchNorm kernels -- forward and parameter gradients against the
+    oracle (fp32, 1e-4), on both sides of the limit."""
     import deepards_b200 as D
-    bb = D.resnet18(initial_planes=16).cuda().train()
-    bb.precision = "fp32"
-    with torch.no_grad():
-        assert tuple(bb(torch.randn(226, 1, 224, device="cuda")).shape) == (226, 128)
-        with pytest.raises(NotImplementedError, match="exceeds the fused stem's limit of 226"):
-            bb(torch.randn(240, 1, 224, device="cuda"))
+    for backbone, kw in (("resnet18", dict(initial_planes=16)), ("densenet18", {})):
+        sd = O.cnn_linear_state(backbone, seed=61, bn_perturb=0.1, **kw)
+        prefix = "breath_block."
+        bsd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+        for n in (226, 300):
+            bb = (D.resnet18(**kw) if backbone == "resnet18" else D.densenet18(drop_rate=0.0))
+            bb.load_state_dict(bsd)
+            bb = bb.cuda().train()
+            bb.precision = "fp32"
+            x = O.synthetic_breaths(n // 20 + 1, seed=9).reshape(-1, 1, 224)[:n]
+            ref = O.backbone_forward(sd, x)              # one BatchNorm group of n breaths
+            got = bb(x.cuda())
+            assert tuple(got.shape) == tuple(ref.shape)
+            assert rel_err(got.detach().cpu(), ref) <= 1e-4, (backbone, n)
+            # gradients of sum(w * features) w.r.t. the stem parameters, torch autograd on the oracle's functional graph
+            w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3))
+            got.backward(w.cuda())
+            names = ["conv1.weight", "bn1.weight", "bn1.bias"] if backbone == "resnet18" else \
+                ["features.conv0.weight", "features.norm0.weight", "features.norm0.bias"]
+            leaves = {k: sd[prefix + k].clone().requires_grad_(True) for k in names}
+            sd2 = dict(sd)
+            sd2.update({prefix + k: v for k, v in leaves.items()})
+            (O.backbone_forward(sd2, x) * w).sum().backward()
+            params = dict(bb.named_parameters())
+            # ReLU / max-pool decisions are not pinned here (tests/test_model_parity_gpu.py explains why two correct fp32
+            # implementations differ by ~1e-3 in whole-network gradients); the chunked stem itself is held to 5e-5 by
+            # tests/test_kernels_gpu.py::test_stem_forward_backward
+            for k in names:
+                err = rel_err(params[k].grad.cpu(), leaves[k].grad)
+                assert err <= 5e-3, (backbone, n, k, err)     # measured 2e-6 .. 2.4e-3 (DenseNet at 226, the fused path: 1.9e-3)
+                print("%s flat batch of %d breaths: d%s rel err %.1e" % (backbone, n, k, err))

@@ -482,9 +482,14 @@ def test_batched_running_update_reduce_rows_and_pack():
         assert torch.equal(kio, r_kio) and torch.equal(koi, r_koi)
 
 
-@pytest.mark.parametrize("c0,group,pool", [(64, 20, 0), (16, 20, 0), (64, 20, 1), (32, 7, 0), (64, 60, 0)])
+@pytest.mark.parametrize("c0,group,pool", [(64, 20, 0), (16, 20, 0), (64, 20, 1), (32, 7, 0), (64, 60, 0),
+                                           (64, 226, 0),     # the largest group of the one-kernel path
+                                           (64, 227, 0),     # chunked path: 3 chunks of 64 + one of 35 breaths
+                                           (32, 300, 1), (16, 640, 0)])
 def test_stem_forward_backward(c0, group, pool):
-    n = group * 3
+    """group <= 226: one fused kernel per direction; above: STATS + APPLY chunk passes forward, PARTIAL + combine backward
+    (a flat batch is one BatchNorm group: ResNet.forward(x) / DenseNet.forward(x) / CNNRegressor)."""
+    n = group * (3 if group <= 226 else 2)
     g = torch.Generator().manual_seed(10)
     x = torch.randn(n, 1, 224, generator=g).to(DEV)
     w = (torch.randn(c0, 1, 7, generator=g) * 0.3).to(DEV).requires_grad_(True)

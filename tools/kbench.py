@@ -132,13 +132,13 @@ def stem():
     def f(i):
         k = i % ROT
         _lib.call("dards_stem_fwd", xs[k].data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), outs[k].data_ptr(),
-                  mean.data_ptr(), rstd.data_ptr(), G, GROUP, c0, c0, 1e-5, 0, _lib.BF16, st())
+                  mean.data_ptr(), rstd.data_ptr(), G, GROUP, c0, c0, 1e-5, 0, None, 0, _lib.BF16, st())
 
     def b(i):
         k = i % ROT
         _lib.call("dards_stem_bwd", outs[k].data_ptr(), xs[k].data_ptr(), w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                   mean.data_ptr(), rstd.data_ptr(), dwp.data_ptr(), dgp.data_ptr(), dbp.data_ptr(), G, GROUP, c0, c0, 0,
-                  _lib.BF16, st())
+                  None, 0, _lib.BF16, st())
 
     print("stem fwd: %6.1f us" % timeit(f))
     print("stem bwd: %6.1f us" % timeit(b), flush=True)
