@@ -912,7 +912,6 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
     p.stages = g_dbg_pair_stages > 0 && g_dbg_pair_stages <= TP_MAX_STAGES ? g_dbg_pair_stages : TP_MAX_STAGES;
     const int pair_smem = tp_smem_bytes(p.stages);
     static int pair_attr = 0;
-    static int pair_clusters = 0;
     if (pair_smem > pair_attr) {
       cudaError_t e = cudaFuncSetAttribute(tc_conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem);
       if (e != cudaSuccess) {
@@ -920,24 +919,10 @@ static int tc_launch(const TcProblem& q, cudaStream_t st) {
         return DARDS_ERR_CUDA;
       }
       pair_attr = pair_smem;
-      // clusters of 2 that can be resident at once (a GPC with an odd number of usable SMs leaves one out)
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * 74);
-      cfg.blockDim = dim3(TC_THREADS);
-      cfg.dynamicSmemBytes = pair_smem;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, tc_conv_pair_kernel, &cfg) != cudaSuccess || nc <= 0) {
-        cudaGetLastError();
-        nc = sm_count() / 2;
-      }
-      pair_clusters = nc;
     }
-    int clusters = pair_clusters < sm_count() / 2 ? pair_clusters : sm_count() / 2;
+    // one cluster of two per TPC; clusters that do not become resident at once simply start when an earlier one ends (the
+    // pairs of different clusters never wait for each other)
+    int clusters = sm_count() / 2;
     if (clusters > tiles / 2) clusters = tiles / 2;
     tc_conv_pair_kernel<<<2 * clusters, TC_THREADS, pair_smem, st>>>(tm_w, tm_x, tm_o, p, lbo, sbo, ver);
     DARDS_CHECK_LAUNCH("tc_conv_pair");
