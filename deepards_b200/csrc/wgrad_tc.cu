@@ -29,7 +29,7 @@
 
 namespace dards {
 
-int g_dbg_wgrad_pair = -1;  // debug key 19 = 1: C >= 256 layers on CTA pairs (cta_group::2)
+int g_dbg_wgrad_pair = -1;  // debug key 19 = 0: C >= 256 layers stay on single CTAs instead of CTA pairs (cta_group::2)
 
 constexpr int WG_TC_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int WG_RMAX = 128;             // reduction rows per stage (multiple of 16)
@@ -432,7 +432,7 @@ static WgPlan wg_plan(int n_breaths, int l_in, int l_out, int c_in, int c_out, i
   // a stage holds 1 or 2 64-channel chunks of each operand: narrow layers get a deeper ring out of the same shared
   // memory (they are load-latency bound: the reduction streams activations straight from HBM)
   p.fuse_taps = (ktaps == 3 && stride == 1 && c_in == 64 && g_dbg_wgrad_fuse != 0) ? 1 : 0;
-  p.pair = (g_dbg_wgrad_pair == 1 && c_out % 256 == 0 && c_in % 128 == 0 && !p.fuse_taps) ? 1 : 0;
+  p.pair = (g_dbg_wgrad_pair != 0 && c_out % 256 == 0 && c_in % 128 == 0 && !p.fuse_taps) ? 1 : 0;
   p.a_bytes = (c_out > 64 ? 2 : 1) * WG_CHUNK_A;
   p.b_bytes = (c_in > 64 && !p.pair ? 2 : 1) * WG_CHUNK_B;
   p.stage_bytes = p.a_bytes + p.n_btiles * p.b_bytes;

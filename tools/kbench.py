@@ -250,11 +250,11 @@ if __name__ == "__main__":
     if os.environ.get("KBENCH_CB_PERTAP"):
         _lib.call("dards_tc_debug_set", 11, int(os.environ["KBENCH_CB_PERTAP"]))
     if os.environ.get("KBENCH_PAIR"):
-        _lib.call("dards_tc_debug_set", 17, int(os.environ["KBENCH_PAIR"]))   # 1: wide layers on the cta_group::2 kernel
+        _lib.call("dards_tc_debug_set", 17, int(os.environ["KBENCH_PAIR"]))   # 0: wide layers on the single-CTA kernel instead of the cta_group::2 one
     if os.environ.get("KBENCH_PAIR_STAGES"):
         _lib.call("dards_tc_debug_set", 18, int(os.environ["KBENCH_PAIR_STAGES"]))
     if os.environ.get("KBENCH_WGRAD_PAIR"):
-        _lib.call("dards_tc_debug_set", 19, int(os.environ["KBENCH_WGRAD_PAIR"]))   # 1: C >= 256 weight gradients on CTA pairs
+        _lib.call("dards_tc_debug_set", 19, int(os.environ["KBENCH_WGRAD_PAIR"]))   # 0: C >= 256 weight gradients on single CTAs instead of CTA pairs
     if os.environ.get("KBENCH_STAGES"):
         _lib.call("dards_tc_debug_set", 6, int(os.environ["KBENCH_STAGES"]))
     for wname in what:
