@@ -312,9 +312,22 @@ typedef struct dards_gradcam_desc {
 int dards_gradcam(const dards_gradcam_desc* desc /* HOST struct, read during the call */, void* stream);
 
 /* ---- debugging ----------------------------------------------------------------------- */
-/* Overrides one field of the tcgen05 shared-memory / instruction descriptors (key: 0 = LBO field,
- * 1 = version field, 2 = SBO field for K-major tiles; 4 = epilogue (0 direct stores, 1 TMA store); 5 = 0 | 1 forces
- * the single-load 3-tap kernel off | on for every k3/s1 layer (default: reductions over <= 128 channels), 6 = 3 pins the operand ring to 3 stages, 7 = 0 issues the 3 wgrad taps of 64-channel layers as 3 MMAs instead of one N = 192 MMA, 8 = 1 opts in to the wave-balanced position-tile width of the wide convolution kernel (measured slower), 9 = 0 loads last-use operands of the backward pass without the L2 evict_first hint, 10 = 1 | 2 routes the wide (> 128 channel) | all k3/s1 convolutions through the main loop of conv_bn_tc.cu (plain store epilogue), 11 = 1 makes the fused conv+BatchNorm kernel load the activations once per tap, 12 = its activation-ring depth, 13 = 1 one 256-column tile per job for its plain mode; value < 0 restores the default).  Only the unit tests and probes use it. */
+/* Kernel-variant switches used by the unit tests, the probes and the A/B measurements in DESIGN.md section 6
+ * (value < 0 restores the default):
+ *    0 / 1 / 2  LBO / version / SBO field of the K-major shared-memory descriptors
+ *    4          epilogue of the per-tap conv kernel: 0 direct stores, 1 TMA store (default)
+ *    5          0 | 1: single-load 3-tap kernel off | on for every k3/s1 layer (default: reductions over <= 128 channels)
+ *    6          3: operand ring pinned to 3 stages
+ *    7          0: the 3 wgrad taps of 64-channel layers as 3 MMAs instead of one N = 192 MMA
+ *    8          1: wave-balanced position-tile width of the wide conv kernel
+ *    9          0: no L2 evict_first hint on last-use operands
+ *   10          1 | 2: wide | all k3/s1 convolutions through the main loop of conv_bn_tc.cu (plain store epilogue)
+ *   11 / 12 / 13 / 14   fused conv+BatchNorm kernel: one activation load per tap / activation-ring depth / one 256-column
+ *              tile per plain job / two sub-tiles share the weight tiles
+ *   15 / 16    grouped BatchNorm: skip the widest tile configurations / resident CTAs chosen for the fullest last wave
+ *   17         0: wide forward / dgrad convolutions on the single-CTA kernel instead of CTA pairs (cta_group::2)
+ *   18         operand-ring depth of the CTA-pair conv kernel (default 6)
+ *   19         0: weight gradients of >= 256-channel layers on single CTAs instead of CTA pairs */
 int dards_tc_debug_set(int key, int value);
 
 #ifdef __cplusplus
