@@ -62,10 +62,10 @@ constexpr int CB_OFF_MOM = 512, CB_OFF_SCSH = CB_OFF_MOM + 16384, CB_OFF_CROW = 
 constexpr int CB_SMEM_LIMIT = 227 * 1024;
 
 enum { CB_PARTIAL = 0, CB_FUSED = 1, CB_PLAIN = 2 };
-int g_dbg_cb_pertap = -1;
-int g_dbg_cb_bstages = -1;
-int g_dbg_cb_wide = -1;
-int g_dbg_cb_share = -1;    // debug key 14 = 1: the job's two sub-tiles are accumulated simultaneously (weight tiles fetched once)     // debug key 13 = 1: plain convolutions use one 256-column tile per job instead of two 160-column ones  // debug key 12: activation-ring depth of the mode3 loop (default 2 chunks)  // debug key 11 = 1: k3/s1 convolutions with BatchNorm use one activation load per tap
+int g_dbg_cb_pertap = -1;   // debug key 11 = 1: k3/s1 convolutions with BatchNorm use one activation load per tap
+int g_dbg_cb_bstages = -1;  // debug key 12: activation-ring depth of the mode3 loop (default 2 chunks)
+int g_dbg_cb_wide = -1;     // debug key 13 = 1: plain convolutions use one 256-column tile per job instead of two 160-column ones
+int g_dbg_cb_share = -1;    // debug key 14 = 1: the job's two sub-tiles are accumulated simultaneously (weight tiles fetched once)
 
 struct CbParams {
   int mode3;
